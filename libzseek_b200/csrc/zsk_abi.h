@@ -1,0 +1,98 @@
+/*
+ * zsk_abi.h — plain-C types shared by the host reader (reader.c), the C-ABI launch layer
+ * (zsk_cuda.cu) and the kernels (zsk_*.cuh).  No CUDA or C++ types appear here.
+ */
+#ifndef ZSK_ABI_H
+#define ZSK_ABI_H
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum { ZSK_CODEC_ZSTD = 0, ZSK_CODEC_LZ4 = 1 }; /* same numbering as zseek_compression_type_t, reference src/zseek.h:121-124 */
+
+/* Per-frame status words written by the decode kernels (0 = ok).  A corrupt or truncated frame makes
+ * zseek_pread return -1 instead of hanging. */
+enum zsk_status {
+    ZSK_ST_OK = 0,
+    ZSK_ST_TRUNC = 1,       /* compressed frame ends early */
+    ZSK_ST_MAGIC = 2,       /* frame does not start with the codec magic */
+    ZSK_ST_FORMAT = 3,      /* reserved bits set / impossible field */
+    ZSK_ST_DST = 4,         /* frame decodes to more bytes than the seek table's dSize */
+    ZSK_ST_OFFSET = 5,      /* match offset reaches before the frame start */
+    ZSK_ST_BITSTREAM = 6,   /* backward bitstream over/under-run */
+    ZSK_ST_TABLE = 7,       /* bad FSE / Huffman description */
+    ZSK_ST_UNSUPPORTED = 8, /* dictionary id */
+    ZSK_ST_SIZE = 9         /* frame decodes to fewer bytes than the seek table's dSize */
+};
+
+/* Device buffers handed to the kernels must be readable ZSK_PAD_FRONT bytes before and ZSK_PAD_BACK
+ * bytes after their logical extent (aligned-word reads of unaligned byte streams). */
+#define ZSK_PAD_FRONT 16
+#define ZSK_PAD_BACK 64
+
+/* zstd: per-CTA literal scratch in HBM (a block regenerates <= 128 KiB of literals) */
+#define ZSK_LIT_SCRATCH (128u * 1024u + 64u)
+
+/* One decode launch works through `njobs` frames.  Job i is frame
+ *     f = frame_ids ? frame_ids[i] : first_frame + i
+ * whose compressed bytes are comp[c_off[f] - comp_base .. c_off[f+1] - comp_base) and whose dSize
+ * bytes go to  dst + (dst_offs ? dst_offs[i] : d_off[f] - dst_base).  All pointers are device pointers. */
+typedef struct zsk_decode_args {
+    const uint64_t *c_off;      /* [N+1] compressed prefix offsets */
+    const uint64_t *d_off;      /* [N+1] decompressed prefix offsets */
+    const uint8_t *comp;        /* device-resident compressed image (slice) */
+    uint64_t comp_base;         /* file offset of comp[0] */
+    const uint32_t *frame_ids;  /* optional [njobs] */
+    const uint64_t *dst_offs;   /* optional [njobs] */
+    uint8_t *dst;
+    uint64_t dst_base;          /* decompressed offset that maps to dst[0] when dst_offs == NULL */
+    uint32_t first_frame;
+    uint32_t njobs;
+    int32_t *status;            /* [njobs] */
+    uint32_t *work_counter;     /* zero-initialised; dynamic job distribution (filled in by the launch layer) */
+    uint8_t *scratch;           /* zstd literal scratch, ZSK_LIT_SCRATCH bytes per CTA (filled in by the launch layer) */
+} zsk_decode_args;
+
+/* K1: batched offset -> frame lookup (semantics of reference src/seek_table.c:187-202 + decompress.c:445) */
+typedef struct zsk_lookup_args {
+    const uint64_t *d_off;   /* [N+1] */
+    uint32_t nframes;
+    const uint64_t *offsets; /* [n] */
+    const uint64_t *counts;  /* [n], or NULL with fixed_count */
+    uint64_t fixed_count;
+    uint32_t n;
+    int32_t *frame;          /* [n] out: frame index or -1 (EOF) */
+    uint32_t *inframe;       /* [n] out */
+    uint32_t *nbytes;        /* [n] out: MIN(count, frame_end - offset) */
+    uint32_t *touched;       /* optional [N] flags: set to 1 for every frame some request needs */
+} zsk_lookup_args;
+
+/* K4: per-request range copy out of decoded frames */
+typedef struct zsk_gather_args {
+    const int32_t *frame;        /* [n] from K1 */
+    const uint32_t *inframe;     /* [n] */
+    const uint32_t *nbytes;      /* [n] */
+    const int64_t *frame_src;    /* [N] byte offset of each decoded frame inside src_base, -1 = absent */
+    const uint8_t *src_base;     /* decoded-frame store (HBM cache slab or a decoded range) */
+    uint8_t *dst;                /* request i lands at dst + (dst_offs ? dst_offs[i] : i * dst_stride) */
+    const uint64_t *dst_offs;
+    uint64_t dst_stride;
+    uint32_t n;
+} zsk_gather_args;
+
+/* frames that are touched by a batch but not resident in the decoded-frame cache */
+typedef struct zsk_compact_args {
+    const uint32_t *touched;   /* [N] */
+    const int64_t *frame_src;  /* [N] */
+    uint32_t nframes;
+    uint32_t *out_ids;         /* [N] */
+    uint32_t *out_count;       /* zero-initialised */
+} zsk_compact_args;
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,329 @@
+/*
+ * zsk_cuda.cu — C-ABI launch layer: device selection, memory, streams, events and the kernel launches.
+ * Compiled by nvcc for sm_100a only (-gencode arch=compute_100a,code=sm_100a).  There is no host
+ * decode path in this file or anywhere else in the library: if no CUDA device is usable,
+ * zsk_cuda_ctx_create fails and zseek_reader_open* reports the error.
+ */
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "zsk_cuda.h"
+#include "zsk_lz4.cuh"
+#include "zsk_zstd.cuh"
+#include "zsk_seek.cuh"
+
+#define ZSK_NCOUNTERS 64
+
+struct zsk_cuda_ctx {
+    int device;
+    int sm_count;
+    cudaStream_t streams[ZSK_NSTREAMS];
+    cudaEvent_t sync_ev;                 /* cross-stream dependencies */
+    cudaEvent_t user_ev[ZSK_NEVENTS];
+    cudaEvent_t t0, t1;                  /* zsk_cuda_timer_* */
+    cudaEvent_t k0, k1;                  /* around the most recent decode kernel */
+    int k_valid;
+    uint32_t *counters;                  /* ZSK_NCOUNTERS work counters, used round-robin */
+    unsigned counter_next;
+    uint8_t *scratch;                    /* zstd literal scratch for zstd_ctas CTAs */
+    int zstd_ctas, lz4_ctas;
+    unsigned long long launches;
+    char err[160];
+};
+
+#define CK(cx, call)                                                                                   \
+    do {                                                                                               \
+        cudaError_t e_ = (call);                                                                       \
+        if (e_ != cudaSuccess) {                                                                       \
+            snprintf((cx)->err, sizeof((cx)->err), "%s: %s", #call, cudaGetErrorString(e_));           \
+            return (int)e_ ? (int)e_ : -1;                                                             \
+        }                                                                                              \
+    } while (0)
+
+extern "C" {
+
+int zsk_cuda_ctx_create(int device, zsk_cuda_ctx **out, char *err, size_t errlen)
+{
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        snprintf(err, errlen, "no CUDA device: %s", e != cudaSuccess ? cudaGetErrorString(e) : "count is 0");
+        return -1;
+    }
+    if (device < 0) {
+        const char *s = getenv("ZSEEK_B200_DEVICE");
+        if (!s) s = getenv("LOCAL_RANK");
+        if (s) device = atoi(s) % ndev;
+        else if (cudaGetDevice(&device) != cudaSuccess) device = 0;
+    }
+    if (device >= ndev) {
+        snprintf(err, errlen, "CUDA device %d out of range (%d present)", device, ndev);
+        return -1;
+    }
+    zsk_cuda_ctx *cx = (zsk_cuda_ctx *)calloc(1, sizeof(*cx));
+    if (!cx) {
+        snprintf(err, errlen, "allocate device context");
+        return -1;
+    }
+    cx->device = device;
+#define CK0(call)                                                                                      \
+    do {                                                                                               \
+        cudaError_t e_ = (call);                                                                       \
+        if (e_ != cudaSuccess) {                                                                       \
+            snprintf(err, errlen, "%s: %s", #call, cudaGetErrorString(e_));                            \
+            free(cx);                                                                                  \
+            return -1;                                                                                 \
+        }                                                                                              \
+    } while (0)
+    CK0(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK0(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) {
+        snprintf(err, errlen, "device %d is sm_%d%d; this library ships sm_100a code only", device, prop.major, prop.minor);
+        free(cx);
+        return -1;
+    }
+    cx->sm_count = prop.multiProcessorCount;
+    for (int i = 0; i < ZSK_NSTREAMS; i++) CK0(cudaStreamCreateWithFlags(&cx->streams[i], cudaStreamNonBlocking));
+    CK0(cudaEventCreateWithFlags(&cx->sync_ev, cudaEventDisableTiming));
+    for (int i = 0; i < ZSK_NEVENTS; i++) CK0(cudaEventCreateWithFlags(&cx->user_ev[i], cudaEventDisableTiming));
+    CK0(cudaEventCreate(&cx->t0));
+    CK0(cudaEventCreate(&cx->t1));
+    CK0(cudaEventCreate(&cx->k0));
+    CK0(cudaEventCreate(&cx->k1));
+    CK0(cudaMalloc((void **)&cx->counters, ZSK_NCOUNTERS * sizeof(uint32_t)));
+    int per_sm = 0;
+    CK0(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, zsk_zstd_decode_kernel, ZSK_ZSTD_CTA_THREADS, 0));
+    if (per_sm < 1) per_sm = 1;
+    cx->zstd_ctas = per_sm * cx->sm_count;
+    CK0(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, zsk_lz4_decode_kernel, ZSK_LZ4_CTA_THREADS, 0));
+    if (per_sm < 1) per_sm = 1;
+    cx->lz4_ctas = per_sm * cx->sm_count;
+    CK0(cudaMalloc((void **)&cx->scratch, (size_t)cx->zstd_ctas * ZSK_LIT_SCRATCH + ZSK_PAD_BACK));
+#undef CK0
+    *out = cx;
+    return 0;
+}
+
+void zsk_cuda_ctx_destroy(zsk_cuda_ctx *cx)
+{
+    if (!cx) return;
+    cudaSetDevice(cx->device);
+    for (int i = 0; i < ZSK_NSTREAMS; i++) {
+        cudaStreamSynchronize(cx->streams[i]);
+        cudaStreamDestroy(cx->streams[i]);
+    }
+    cudaEventDestroy(cx->sync_ev);
+    for (int i = 0; i < ZSK_NEVENTS; i++) cudaEventDestroy(cx->user_ev[i]);
+    cudaEventDestroy(cx->t0);
+    cudaEventDestroy(cx->t1);
+    cudaEventDestroy(cx->k0);
+    cudaEventDestroy(cx->k1);
+    cudaFree(cx->counters);
+    cudaFree(cx->scratch);
+    free(cx);
+}
+
+const char *zsk_cuda_error(zsk_cuda_ctx *cx) { return cx ? cx->err : "no device context"; }
+int zsk_cuda_device(const zsk_cuda_ctx *cx) { return cx->device; }
+int zsk_cuda_sm_count(const zsk_cuda_ctx *cx) { return cx->sm_count; }
+unsigned long long zsk_cuda_launch_count(const zsk_cuda_ctx *cx) { return cx->launches; }
+
+size_t zsk_cuda_free_memory(zsk_cuda_ctx *cx)
+{
+    size_t fr = 0, tot = 0;
+    cudaSetDevice(cx->device);
+    if (cudaMemGetInfo(&fr, &tot) != cudaSuccess) return 0;
+    return fr;
+}
+
+int zsk_cuda_malloc(zsk_cuda_ctx *cx, void **p, size_t n)
+{
+    CK(cx, cudaSetDevice(cx->device));
+    CK(cx, cudaMalloc(p, n ? n : 1));
+    return 0;
+}
+
+int zsk_cuda_free(zsk_cuda_ctx *cx, void *p)
+{
+    if (!p) return 0;
+    CK(cx, cudaSetDevice(cx->device));
+    CK(cx, cudaFree(p));
+    return 0;
+}
+
+int zsk_cuda_malloc_host(zsk_cuda_ctx *cx, void **p, size_t n)
+{
+    CK(cx, cudaSetDevice(cx->device));
+    CK(cx, cudaHostAlloc(p, n ? n : 1, cudaHostAllocDefault));
+    return 0;
+}
+
+int zsk_cuda_free_host(zsk_cuda_ctx *cx, void *p)
+{
+    if (!p) return 0;
+    CK(cx, cudaFreeHost(p));
+    return 0;
+}
+
+int zsk_cuda_memset_async(zsk_cuda_ctx *cx, void *p, int v, size_t n, int stream)
+{
+    CK(cx, cudaSetDevice(cx->device));
+    CK(cx, cudaMemsetAsync(p, v, n, cx->streams[stream]));
+    return 0;
+}
+
+int zsk_cuda_memcpy_async(zsk_cuda_ctx *cx, void *dst, const void *src, size_t n, int kind, int stream)
+{
+    if (n == 0) return 0;
+    cudaMemcpyKind k = kind == ZSK_H2D ? cudaMemcpyHostToDevice : kind == ZSK_D2H ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+    CK(cx, cudaSetDevice(cx->device));
+    CK(cx, cudaMemcpyAsync(dst, src, n, k, cx->streams[stream]));
+    return 0;
+}
+
+int zsk_cuda_stream_sync(zsk_cuda_ctx *cx, int stream)
+{
+    CK(cx, cudaStreamSynchronize(cx->streams[stream]));
+    return 0;
+}
+
+int zsk_cuda_stream_wait(zsk_cuda_ctx *cx, int waiter, int signaler)
+{
+    CK(cx, cudaSetDevice(cx->device));
+    CK(cx, cudaEventRecord(cx->sync_ev, cx->streams[signaler]));
+    CK(cx, cudaStreamWaitEvent(cx->streams[waiter], cx->sync_ev, 0));
+    return 0;
+}
+
+int zsk_cuda_event_record(zsk_cuda_ctx *cx, int ev, int stream)
+{
+    CK(cx, cudaSetDevice(cx->device));
+    CK(cx, cudaEventRecord(cx->user_ev[ev], cx->streams[stream]));
+    return 0;
+}
+
+int zsk_cuda_event_sync(zsk_cuda_ctx *cx, int ev)
+{
+    CK(cx, cudaEventSynchronize(cx->user_ev[ev]));
+    return 0;
+}
+
+int zsk_cuda_pointer_is_device(zsk_cuda_ctx *cx, const void *p)
+{
+    cudaPointerAttributes at;
+    cudaError_t e = cudaPointerGetAttributes(&at, p);
+    if (e != cudaSuccess) {
+        cudaGetLastError(); /* unregistered host memory reports an error on old runtimes */
+        return 0;
+    }
+    (void)cx;
+    return (at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged) ? 1 : 0;
+}
+
+static int next_counter(zsk_cuda_ctx *cx, int stream, uint32_t **out)
+{
+    uint32_t *c = cx->counters + (cx->counter_next++ % ZSK_NCOUNTERS);
+    CK(cx, cudaMemsetAsync(c, 0, sizeof(uint32_t), cx->streams[stream]));
+    *out = c;
+    return 0;
+}
+
+int zsk_cuda_launch_decode(zsk_cuda_ctx *cx, int codec, const zsk_decode_args *args, int stream)
+{
+    if (args->njobs == 0) return 0;
+    CK(cx, cudaSetDevice(cx->device));
+    zsk_decode_args a = *args;
+    int rc = next_counter(cx, stream, &a.work_counter);
+    if (rc) return rc;
+    a.scratch = cx->scratch;
+    cudaStream_t s = cx->streams[stream];
+    CK(cx, cudaEventRecord(cx->k0, s));
+    if (codec == ZSK_CODEC_LZ4) {
+        const unsigned warps_per_cta = ZSK_LZ4_CTA_THREADS / 32;
+        unsigned ctas = (a.njobs + warps_per_cta - 1) / warps_per_cta;
+        if (ctas > (unsigned)cx->lz4_ctas) ctas = (unsigned)cx->lz4_ctas;
+        zsk_lz4_decode_kernel<<<ctas, ZSK_LZ4_CTA_THREADS, 0, s>>>(a);
+    } else if (codec == ZSK_CODEC_ZSTD) {
+        unsigned ctas = a.njobs < (unsigned)cx->zstd_ctas ? a.njobs : (unsigned)cx->zstd_ctas;
+        zsk_zstd_decode_kernel<<<ctas, ZSK_ZSTD_CTA_THREADS, 0, s>>>(a);
+    } else {
+        snprintf(cx->err, sizeof(cx->err), "unknown codec %d", codec);
+        return -1;
+    }
+    CK(cx, cudaGetLastError());
+    CK(cx, cudaEventRecord(cx->k1, s));
+    cx->k_valid = 1;
+    cx->launches++;
+    return 0;
+}
+
+static unsigned grid_for(zsk_cuda_ctx *cx, uint64_t threads_wanted, unsigned block)
+{
+    uint64_t ctas = (threads_wanted + block - 1) / block;
+    uint64_t cap = (uint64_t)cx->sm_count * 8;
+    if (ctas > cap) ctas = cap;
+    if (ctas < 1) ctas = 1;
+    return (unsigned)ctas;
+}
+
+int zsk_cuda_launch_lookup(zsk_cuda_ctx *cx, const zsk_lookup_args *args, int stream)
+{
+    if (args->n == 0) return 0;
+    CK(cx, cudaSetDevice(cx->device));
+    zsk_lookup_kernel<<<grid_for(cx, args->n, 256), 256, 0, cx->streams[stream]>>>(*args);
+    CK(cx, cudaGetLastError());
+    cx->launches++;
+    return 0;
+}
+
+int zsk_cuda_launch_gather(zsk_cuda_ctx *cx, const zsk_gather_args *args, int stream)
+{
+    if (args->n == 0) return 0;
+    CK(cx, cudaSetDevice(cx->device));
+    zsk_gather_kernel<<<grid_for(cx, (uint64_t)args->n * 32, 256), 256, 0, cx->streams[stream]>>>(*args);
+    CK(cx, cudaGetLastError());
+    cx->launches++;
+    return 0;
+}
+
+int zsk_cuda_launch_compact(zsk_cuda_ctx *cx, const zsk_compact_args *args, int stream)
+{
+    if (args->nframes == 0) return 0;
+    CK(cx, cudaSetDevice(cx->device));
+    zsk_compact_kernel<<<grid_for(cx, args->nframes, 256), 256, 0, cx->streams[stream]>>>(*args);
+    CK(cx, cudaGetLastError());
+    cx->launches++;
+    return 0;
+}
+
+int zsk_cuda_timer_start(zsk_cuda_ctx *cx, int stream)
+{
+    CK(cx, cudaSetDevice(cx->device));
+    CK(cx, cudaEventRecord(cx->t0, cx->streams[stream]));
+    return 0;
+}
+
+int zsk_cuda_timer_stop(zsk_cuda_ctx *cx, int stream, float *ms)
+{
+    CK(cx, cudaSetDevice(cx->device));
+    CK(cx, cudaEventRecord(cx->t1, cx->streams[stream]));
+    CK(cx, cudaEventSynchronize(cx->t1));
+    CK(cx, cudaEventElapsedTime(ms, cx->t0, cx->t1));
+    return 0;
+}
+
+int zsk_cuda_last_decode_ms(zsk_cuda_ctx *cx, float *ms)
+{
+    if (!cx->k_valid) {
+        snprintf(cx->err, sizeof(cx->err), "no decode kernel launched yet");
+        return -1;
+    }
+    CK(cx, cudaEventSynchronize(cx->k1));
+    CK(cx, cudaEventElapsedTime(ms, cx->k0, cx->k1));
+    return 0;
+}
+
+} /* extern "C" */

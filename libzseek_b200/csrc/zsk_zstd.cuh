@@ -1,0 +1,600 @@
+/*
+ * zsk_zstd.cuh — K3: zstd frame decode, ONE CTA PER FRAME (replaces the reference's calls into libzstd:
+ * ZSTD_decompressDCtx at reference src/decompress.c:537 and ZSTD_decompressStream at :434,:448;
+ * format: RFC 8878 as restated in SURVEY.md Appendix A.2).
+ *
+ * CTA = 2 warps with fixed roles, so the two serial chains of a compressed block overlap:
+ *
+ *   warp 0 ("literals + execute")              warp 1 ("sequences")
+ *   ------------------------------------       ---------------------------------------------
+ *   Huffman tree description -> weights         FSE table descriptions -> LL/OF/ML decode tables
+ *   parallel fill of the 2^maxBits table        (Predefined / RLE / FSE_Compressed / Repeat)
+ *   lanes 0..3 decode the 4 Huffman streams
+ *   ------------------------------ __syncthreads ------------------------------
+ *   executes sequence chunk c-1:                lane 0 decodes sequence chunk c from the backward
+ *   literal copy + match copy, 32 lanes         bitstream (3 interleaved FSE states), resolves
+ *   cooperating, warp-level sync only           repeat-offsets, writes {LL, ML, offset} to smem
+ *   ------------------------------ __syncthreads (per chunk) ------------------
+ *
+ * All tables live in shared memory (Huffman 4 KiB, FSE 5 KiB, two sequence chunks 6 KiB); Huffman
+ * output goes to a per-CTA literal scratch in HBM (L2-resident, <= 128 KiB), the frame's output is
+ * written straight to its final place and re-read from L1/L2 for match copies (offsets reach up to
+ * the whole frame, far beyond what shared memory could hold for 256 KiB - 1 MiB frames).
+ * Cross-block state (repeat offsets, previous Huffman table, previous FSE tables) stays in shared
+ * memory for the life of the frame.  Persistent CTAs pull frames from a global atomic counter.
+ */
+#pragma once
+#include "zsk_common.cuh"
+
+#define ZSK_ZSTD_MAGIC 0xFD2FB528u
+#define ZSK_ZSTD_CTA_THREADS 64
+#define ZSK_SEQ_CHUNK 256
+#define ZSK_BLOCK_MAX (128u << 10)
+
+struct zsk_zstd_smem {
+    uint16_t huf[2048];                   /* sym | nbBits << 8 */
+    uint32_t fse_ll[512];                 /* sym | nbBits << 8 | base << 16 */
+    uint32_t fse_ml[512];
+    uint32_t fse_of[256];
+    uint32_t wtab[64];                    /* FSE table of the Huffman weights */
+    uint32_t seq[2][ZSK_SEQ_CHUNK][3];    /* literal length, match length, offset */
+    uint16_t huf_start[256];
+    uint8_t weights[256];
+    int16_t probs[64];                    /* sequence-table build scratch (warp 1) */
+    uint16_t next[64];
+    int16_t probs_w[16];                  /* Huffman-weight table build scratch (warp 0) */
+    uint16_t next_w[16];
+    uint32_t rep[3];
+    int32_t log_ll, log_ml, log_of, log_huf; /* -1 = table not valid yet */
+    int32_t err;                          /* first error of the frame; read only after __syncthreads_or */
+    uint32_t bs_start;                    /* start of the sequence bitstream inside the block */
+    uint32_t op;                          /* block output position handed from warp 0 to the CTA */
+    uint32_t job;
+};
+
+/* CTA-uniform error exchange: every thread passes its own status; if any is non-zero all threads
+ * get the same non-zero status back (the barrier also orders shared-memory traffic). */
+static __device__ __forceinline__ int zsk_cta_status(zsk_zstd_smem &S, int st)
+{
+    if (st) S.err = st;
+    return __syncthreads_or(st) ? S.err : ZSK_ST_OK;
+}
+
+/* ---- backward bitstream reader (see SURVEY.md Appendix A.2 "Backward bitstreams") ---- */
+struct zsk_bits {
+    const uint8_t *base;
+    int32_t pos;   /* number of unread bits; goes negative on over-read (reads then yield zeros) */
+    int32_t wbase; /* stream bit index of win bit 0 */
+    uint64_t win;
+};
+
+static __device__ __forceinline__ void zsk_bits_refill(zsk_bits &b)
+{
+    int32_t byteoff = ((b.pos + 7) >> 3) - 8;
+    b.wbase = byteoff * 8;
+    if (byteoff >= 0) b.win = zsk_ld64_unaligned(b.base + byteoff);
+    else if (byteoff <= -8) b.win = 0;
+    else b.win = zsk_ld64_unaligned(b.base) << (unsigned)(-byteoff * 8);
+}
+
+static __device__ __forceinline__ int zsk_bits_init(zsk_bits &b, const uint8_t *p, uint32_t n)
+{
+    if (n == 0) return ZSK_ST_BITSTREAM;
+    uint32_t last = ZSK_LDG(p + n - 1);
+    if (last == 0) return ZSK_ST_BITSTREAM;
+    b.base = p;
+    b.pos = (int32_t)(n - 1) * 8 + (31 - __clz((int)last));
+    zsk_bits_refill(b);
+    return ZSK_ST_OK;
+}
+
+static __device__ __forceinline__ uint32_t zsk_bits_read(zsk_bits &b, uint32_t n) /* n <= 32 */
+{
+    if (b.pos - (int32_t)n < b.wbase) zsk_bits_refill(b);
+    b.pos -= (int32_t)n;
+    uint64_t v = b.win >> (unsigned)(b.pos - b.wbase);
+    return (uint32_t)v & (uint32_t)((1ull << n) - 1);
+}
+
+static __device__ __forceinline__ int zsk_bitlen(uint32_t v) { return 32 - __clz((int)v); }
+
+/* ---- FSE table description (forward bitstream). Single thread. Returns bytes consumed (>0) or -status. */
+static __device__ int zsk_fse_read_ncount(const uint8_t *p, uint32_t n, int max_log, int max_sym, int16_t *probs,
+                                          int *nsym, int *log_out)
+{
+    if (n == 0) return -ZSK_ST_TRUNC;
+    uint32_t bitpos = 0;
+    int al = 5 + (int)(zsk_ld32_unaligned(p) & 15);
+    bitpos = 4;
+    if (al > max_log) return -ZSK_ST_TABLE;
+    int remaining = 1 << al, s = 0;
+    while (remaining > 0) {
+        if (s > max_sym) return -ZSK_ST_TABLE;
+        int bits = zsk_bitlen((uint32_t)(remaining + 1));
+        uint32_t val = (zsk_ld32_unaligned(p + (bitpos >> 3)) >> (bitpos & 7)) & ((1u << bits) - 1);
+        uint32_t low = (1u << (bits - 1)) - 1;
+        uint32_t thr = (1u << bits) - 1 - (uint32_t)(remaining + 1);
+        if ((val & low) < thr) { val &= low; bitpos += (uint32_t)bits - 1; }
+        else { if (val > low) val -= thr; bitpos += (uint32_t)bits; }
+        int prob = (int)val - 1;
+        probs[s++] = (int16_t)prob;
+        remaining -= prob < 0 ? -prob : prob;
+        if (prob == 0) {
+            for (;;) {
+                uint32_t rep = (zsk_ld32_unaligned(p + (bitpos >> 3)) >> (bitpos & 7)) & 3;
+                bitpos += 2;
+                for (uint32_t i = 0; i < rep; i++) { if (s > max_sym) return -ZSK_ST_TABLE; probs[s++] = 0; }
+                if (rep != 3) break;
+                if ((bitpos + 7) / 8 > n) return -ZSK_ST_TRUNC;
+            }
+        }
+        if ((bitpos + 7) / 8 > n) return -ZSK_ST_TRUNC;
+    }
+    if (remaining != 0) return -ZSK_ST_TABLE;
+    *nsym = s;
+    *log_out = al;
+    return (int)((bitpos + 7) / 8);
+}
+
+/* ---- FSE decode-table build. Single thread. tab entries: sym | nb << 8 | base << 16. */
+static __device__ int zsk_fse_build(uint32_t *tab, const int16_t *probs, int nsym, int log, uint16_t *next)
+{
+    const int size = 1 << log;
+    int high = size - 1;
+    for (int s = 0; s < nsym; s++) {
+        if (probs[s] == -1) { tab[high--] = (uint32_t)s; next[s] = 1; }
+        else next[s] = (uint16_t)probs[s];
+    }
+    const int step = (size >> 1) + (size >> 3) + 3, mask = size - 1;
+    int pos = 0;
+    for (int s = 0; s < nsym; s++)
+        for (int i = 0; i < probs[s]; i++) {
+            tab[pos] = (uint32_t)s;
+            do { pos = (pos + step) & mask; } while (pos > high);
+        }
+    if (pos != 0) return ZSK_ST_TABLE;
+    for (int i = 0; i < size; i++) {
+        uint32_t s = tab[i];
+        uint32_t d = next[s]++;
+        uint32_t nb = (uint32_t)(log - (zsk_bitlen(d) - 1));
+        tab[i] = s | (nb << 8) | ((((d << nb) - (uint32_t)size) & 0xffffu) << 16);
+    }
+    return ZSK_ST_OK;
+}
+
+/* predefined distributions, RFC 8878 3.1.1.3.2.2 */
+static __device__ const int16_t ZSK_LL_DEF[36] = { 4,3,2,2,2,2,2,2,2,2,2,2,2,1,1,1,2,2,2,2,2,2,2,2,2,3,2,1,1,1,1,1,-1,-1,-1,-1 };
+static __device__ const int16_t ZSK_ML_DEF[53] = { 1,4,3,2,2,2,2,2,2,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,-1,-1,-1,-1,-1,-1,-1 };
+static __device__ const int16_t ZSK_OF_DEF[29] = { 1,1,1,1,1,1,2,2,2,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,-1,-1,-1,-1,-1 };
+static __device__ const uint32_t ZSK_LL_BASE[36] = { 0,1,2,3,4,5,6,7,8,9,10,11,12,13,14,15,16,18,20,22,24,28,32,40,48,64,128,256,512,1024,2048,4096,8192,16384,32768,65536 };
+static __device__ const uint8_t ZSK_LL_BITS[36] = { 0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,1,1,1,1,2,2,3,3,4,6,7,8,9,10,11,12,13,14,15,16 };
+static __device__ const uint32_t ZSK_ML_BASE[53] = { 3,4,5,6,7,8,9,10,11,12,13,14,15,16,17,18,19,20,21,22,23,24,25,26,27,28,29,30,31,32,33,34,35,37,39,41,43,47,51,59,67,83,99,131,259,515,1027,2051,4099,8195,16387,32771,65539 };
+static __device__ const uint8_t ZSK_ML_BITS[53] = { 0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,1,1,1,1,2,2,3,3,4,4,5,7,8,9,10,11,12,13,14,15,16 };
+
+/* One of the three sequence tables.  Single thread.  Advances *ip past the description. */
+static __device__ int zsk_seq_table(uint32_t *tab, int32_t *log_io, int mode, const uint8_t *p, uint32_t n, uint32_t *ip,
+                                    const int16_t *def, int def_n, int def_log, int max_log, int max_sym,
+                                    int16_t *probs, uint16_t *next)
+{
+    if (mode == 0) {
+        for (int i = 0; i < def_n; i++) probs[i] = def[i];
+        int r = zsk_fse_build(tab, probs, def_n, def_log, next);
+        if (r) return r;
+        *log_io = def_log;
+        return ZSK_ST_OK;
+    }
+    if (mode == 1) {
+        if (*ip >= n) return ZSK_ST_TRUNC;
+        uint32_t sym = ZSK_LDG(p + *ip);
+        if ((int)sym > max_sym) return ZSK_ST_TABLE;
+        *ip += 1;
+        tab[0] = sym; /* 0 bits, base 0 */
+        *log_io = 0;
+        return ZSK_ST_OK;
+    }
+    if (mode == 2) {
+        int nsym, log;
+        int used = zsk_fse_read_ncount(p + *ip, n - *ip, max_log, max_sym, probs, &nsym, &log);
+        if (used < 0) return -used;
+        int r = zsk_fse_build(tab, probs, nsym, log, next);
+        if (r) return r;
+        *ip += (uint32_t)used;
+        *log_io = log;
+        return ZSK_ST_OK;
+    }
+    return *log_io >= 0 ? ZSK_ST_OK : ZSK_ST_TABLE; /* Repeat */
+}
+
+/* ---- Huffman tree description -> weights[] (incl. the implicit last one).  Single thread.
+ * Returns bytes consumed (>0) or -status; sets *nw and *max_bits. */
+static __device__ int zsk_huf_read_weights(zsk_zstd_smem &S, const uint8_t *p, uint32_t n, int *nw_out, int *max_bits_out)
+{
+    if (n < 1) return -ZSK_ST_TRUNC;
+    uint8_t *w = S.weights;
+    int nw = 0;
+    const uint32_t hb = ZSK_LDG(p);
+    uint32_t used;
+    if (hb >= 128) {
+        nw = (int)hb - 127;
+        const uint32_t bytes = ((uint32_t)nw + 1) / 2;
+        if (1 + bytes > n) return -ZSK_ST_TRUNC;
+        for (int i = 0; i < nw; i++) {
+            uint32_t b = ZSK_LDG(p + 1 + i / 2);
+            w[i] = (uint8_t)((i & 1) ? (b & 15) : (b >> 4));
+        }
+        used = 1 + bytes;
+    } else {
+        if (hb == 0 || 1 + hb > n) return -ZSK_ST_TRUNC;
+        int nsym, log;
+        int hdr = zsk_fse_read_ncount(p + 1, hb, 6, 12, S.probs_w, &nsym, &log);
+        if (hdr < 0) return hdr;
+        int r = zsk_fse_build(S.wtab, S.probs_w, nsym, log, S.next_w);
+        if (r) return -r;
+        if ((uint32_t)hdr >= hb) return -ZSK_ST_TRUNC;
+        zsk_bits b;
+        r = zsk_bits_init(b, p + 1 + hdr, hb - (uint32_t)hdr);
+        if (r) return -r;
+        uint32_t s1 = zsk_bits_read(b, (uint32_t)log), s2 = zsk_bits_read(b, (uint32_t)log);
+        for (;;) {
+            if (nw > 253) return -ZSK_ST_TABLE;
+            uint32_t e1 = S.wtab[s1];
+            w[nw++] = (uint8_t)e1;
+            s1 = (e1 >> 16) + zsk_bits_read(b, (e1 >> 8) & 0xff);
+            if (b.pos < 0) { w[nw++] = (uint8_t)S.wtab[s2]; break; }
+            uint32_t e2 = S.wtab[s2];
+            w[nw++] = (uint8_t)e2;
+            s2 = (e2 >> 16) + zsk_bits_read(b, (e2 >> 8) & 0xff);
+            if (b.pos < 0) { w[nw++] = (uint8_t)S.wtab[s1]; break; }
+        }
+        used = 1 + hb;
+    }
+    uint32_t total = 0;
+    for (int i = 0; i < nw; i++) {
+        if (w[i] > 12) return -ZSK_ST_TABLE;
+        if (w[i]) total += 1u << (w[i] - 1);
+    }
+    if (total == 0) return -ZSK_ST_TABLE;
+    const int max_bits = zsk_bitlen(total);
+    if (max_bits > 11) return -ZSK_ST_TABLE;
+    const uint32_t rest = (1u << max_bits) - total;
+    if (rest == 0 || (rest & (rest - 1))) return -ZSK_ST_TABLE;
+    w[nw++] = (uint8_t)zsk_bitlen(rest);
+    /* table start of every symbol: codes of decreasing length first, symbols in increasing order */
+    uint32_t cnt[13], idx[13];
+    for (int i = 0; i < 13; i++) cnt[i] = 0;
+    for (int i = 0; i < nw; i++) if (w[i]) cnt[max_bits + 1 - w[i]]++;
+    idx[max_bits] = 0;
+    for (int L = max_bits; L >= 1; L--) idx[L - 1] = idx[L] + cnt[L] * (1u << (max_bits - L));
+    for (int s = 0; s < nw; s++) {
+        if (!w[s]) continue;
+        int nbits = max_bits + 1 - w[s];
+        S.huf_start[s] = (uint16_t)idx[nbits];
+        idx[nbits] += 1u << (max_bits - nbits);
+    }
+    *nw_out = nw;
+    *max_bits_out = max_bits;
+    return (int)used;
+}
+
+/* One Huffman stream, one lane: regenerates nout bytes into out. */
+static __device__ int zsk_huf_stream(const uint16_t *tab, int log, const uint8_t *p, uint32_t n, uint8_t *out, uint32_t nout)
+{
+    zsk_bits b;
+    int r = zsk_bits_init(b, p, n);
+    if (r) return r;
+    const uint32_t mask = (1u << log) - 1;
+    uint32_t state = zsk_bits_read(b, (uint32_t)log);
+    for (uint32_t i = 0; i < nout; i++) {
+        uint32_t e = tab[state];
+        out[i] = (uint8_t)e;
+        uint32_t nb = e >> 8;
+        state = ((state << nb) | zsk_bits_read(b, nb)) & mask;
+    }
+    return b.pos == -log ? ZSK_ST_OK : ZSK_ST_BITSTREAM;
+}
+
+/* Literal source of a block, as the executing warp sees it. */
+struct zsk_lits {
+    const uint8_t *ptr; /* raw bytes (compressed stream or Huffman scratch); NULL for RLE */
+    uint32_t rle;
+    uint32_t size;
+};
+
+static __device__ __forceinline__ void zsk_warp_literals(uint8_t *dst, const zsk_lits &L, uint32_t lpos, uint32_t n, unsigned lane)
+{
+    if (L.ptr) {
+        if (n <= 32) { if (lane < n) dst[lane] = L.ptr[lpos + lane]; }
+        else zsk_group_copy(dst, L.ptr + lpos, n, lane, 32);
+    } else {
+        zsk_group_fill(dst, (uint8_t)L.rle, n, lane, 32);
+    }
+}
+
+/*
+ * One compressed block.  p[0..n) is the block content.  All threads of the CTA call this with
+ * identical arguments; returns the (CTA-uniform) status.  *pop is advanced by the block's output.
+ */
+static __device__ int zsk_zstd_block(zsk_zstd_smem &S, const uint8_t *__restrict__ p, uint32_t n, uint8_t *out, uint32_t *pop,
+                                     uint32_t cap, uint8_t *lit_scratch)
+{
+    const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    /* ---------------- literals section header (uniform) */
+    if (n < 1) return ZSK_ST_TRUNC;
+    const uint32_t b0 = ZSK_LDG(p), ltype = b0 & 3, sf = (b0 >> 2) & 3;
+    uint32_t regen, comp = 0, hsize, streams = 1;
+    if (ltype < 2) {
+        if (sf == 0 || sf == 2) { regen = b0 >> 3; hsize = 1; }
+        else if (sf == 1) { if (n < 2) return ZSK_ST_TRUNC; regen = (b0 >> 4) + ((uint32_t)ZSK_LDG(p + 1) << 4); hsize = 2; }
+        else { if (n < 3) return ZSK_ST_TRUNC; regen = (b0 >> 4) + ((uint32_t)ZSK_LDG(p + 1) << 4) + ((uint32_t)ZSK_LDG(p + 2) << 12); hsize = 3; }
+    } else {
+        uint32_t bits;
+        if (sf == 0) { hsize = 3; bits = 10; }
+        else if (sf == 1) { hsize = 3; bits = 10; streams = 4; }
+        else if (sf == 2) { hsize = 4; bits = 14; streams = 4; }
+        else { hsize = 5; bits = 18; streams = 4; }
+        if (n < hsize) return ZSK_ST_TRUNC;
+        uint64_t v = 0;
+        for (uint32_t i = 0; i < hsize; i++) v |= (uint64_t)ZSK_LDG(p + i) << (8 * i);
+        regen = (uint32_t)(v >> 4) & ((1u << bits) - 1);
+        comp = (uint32_t)(v >> (4 + bits));
+    }
+    if (regen > ZSK_BLOCK_MAX) return ZSK_ST_FORMAT;
+    uint32_t ip = hsize; /* start of literal payload */
+    zsk_lits L;
+    L.size = regen; L.rle = 0; L.ptr = nullptr;
+    uint32_t seq_ip; /* start of the sequences section */
+    if (ltype == 0) { if (regen > n - ip) return ZSK_ST_TRUNC; L.ptr = p + ip; seq_ip = ip + regen; }
+    else if (ltype == 1) { if (n - ip < 1) return ZSK_ST_TRUNC; L.rle = ZSK_LDG(p + ip); seq_ip = ip + 1; }
+    else { if (comp > n - ip) return ZSK_ST_TRUNC; L.ptr = lit_scratch; seq_ip = ip + comp; }
+
+    /* ---------------- sequences section header (uniform) */
+    if (seq_ip >= n) return ZSK_ST_TRUNC;
+    uint32_t sp = seq_ip;
+    uint32_t nseq = ZSK_LDG(p + sp);
+    sp++;
+    if (nseq >= 128) {
+        if (nseq == 255) { if (n - sp < 2) return ZSK_ST_TRUNC; nseq = zsk_rd16(p + sp) + 0x7F00; sp += 2; }
+        else { if (n - sp < 1) return ZSK_ST_TRUNC; nseq = ((nseq - 128) << 8) + ZSK_LDG(p + sp); sp += 1; }
+    }
+    uint32_t modes = 0;
+    if (nseq) {
+        if (sp >= n) return ZSK_ST_TRUNC;
+        modes = ZSK_LDG(p + sp);
+        sp++;
+        if (modes & 3) return ZSK_ST_FORMAT;
+    }
+
+    /* ---------------- stage 1: warp 0 regenerates literals, warp 1 builds the sequence tables */
+    int st = ZSK_ST_OK;
+    if (warp == 0) {
+        if (ltype >= 2) {
+            const uint8_t *q = p + ip;
+            uint32_t qn = comp;
+            int nw = 0, max_bits = 0;
+            if (ltype == 2) {
+                int used = 0;
+                if (lane == 0) {
+                    used = zsk_huf_read_weights(S, q, qn, &nw, &max_bits);
+                    if (used < 0) st = -used; else S.log_huf = max_bits;
+                }
+                __syncwarp(); /* weights[], huf_start[], log_huf visible to the warp */
+                st = __shfl_sync(ZSK_FULL, st, 0);
+                used = __shfl_sync(ZSK_FULL, used, 0);
+                nw = __shfl_sync(ZSK_FULL, nw, 0);
+                max_bits = __shfl_sync(ZSK_FULL, max_bits, 0);
+                if (st == ZSK_ST_OK) {
+                    for (int s = (int)lane; s < nw; s += 32) {
+                        uint32_t w = S.weights[s];
+                        if (!w) continue;
+                        uint32_t nbits = (uint32_t)max_bits + 1 - w, run = 1u << (w - 1), start = S.huf_start[s];
+                        uint16_t e = (uint16_t)((uint32_t)s | (nbits << 8));
+                        for (uint32_t i = 0; i < run; i++) S.huf[start + i] = e;
+                    }
+                    q += used;
+                    qn -= (uint32_t)used;
+                }
+                __syncwarp();
+            } else if (S.log_huf < 0) st = ZSK_ST_TABLE;
+            if (st == ZSK_ST_OK) {
+                const int log = S.log_huf;
+                if (streams == 1) {
+                    if (lane == 0) st = zsk_huf_stream(S.huf, log, q, qn, lit_scratch, regen);
+                } else {
+                    if (qn < 6) st = ZSK_ST_TRUNC;
+                    else {
+                        const uint32_t s1 = zsk_rd16(q), s2 = zsk_rd16(q + 2), s3 = zsk_rd16(q + 4);
+                        const uint32_t per = (regen + 3) / 4;
+                        if (6 + s1 + s2 + s3 > qn) st = ZSK_ST_TRUNC;
+                        else if (3 * per > regen) st = ZSK_ST_FORMAT;
+                        else if (lane < 4) {
+                            const uint32_t s4 = qn - 6 - s1 - s2 - s3;
+                            const uint32_t soff = lane == 0 ? 0 : lane == 1 ? s1 : lane == 2 ? s1 + s2 : s1 + s2 + s3;
+                            const uint32_t slen = lane == 0 ? s1 : lane == 1 ? s2 : lane == 2 ? s3 : s4;
+                            const uint32_t nout = lane < 3 ? per : regen - 3 * per;
+                            st = zsk_huf_stream(S.huf, log, q + 6 + soff, slen, lit_scratch + lane * per, nout);
+                        }
+                    }
+                }
+            }
+        }
+    } else if (lane == 0 && nseq) {
+        st = zsk_seq_table(S.fse_ll, &S.log_ll, (modes >> 6) & 3, p, n, &sp, ZSK_LL_DEF, 36, 6, 9, 35, S.probs, S.next);
+        if (!st) st = zsk_seq_table(S.fse_of, &S.log_of, (modes >> 4) & 3, p, n, &sp, ZSK_OF_DEF, 29, 5, 8, 31, S.probs, S.next);
+        if (!st) st = zsk_seq_table(S.fse_ml, &S.log_ml, (modes >> 2) & 3, p, n, &sp, ZSK_ML_DEF, 53, 6, 9, 52, S.probs, S.next);
+        S.bs_start = sp;
+    }
+    if ((st = zsk_cta_status(S, st))) return st;
+
+    /* ---------------- stage 2: sequence decode (warp 1 lane 0) overlapped with execution (warp 0) */
+    uint32_t op = *pop, lpos = 0;
+    if (nseq) {
+        zsk_bits b;
+        uint32_t sl = 0, so = 0, sm = 0;
+        if (tid == 32) {
+            sp = S.bs_start;
+            st = sp < n ? zsk_bits_init(b, p + sp, n - sp) : ZSK_ST_TRUNC;
+            if (!st) {
+                sl = zsk_bits_read(b, (uint32_t)S.log_ll);
+                so = zsk_bits_read(b, (uint32_t)S.log_of);
+                sm = zsk_bits_read(b, (uint32_t)S.log_ml);
+            }
+        }
+        const uint32_t nchunks = (nseq + ZSK_SEQ_CHUNK - 1) / ZSK_SEQ_CHUNK;
+        for (uint32_t c = 0; c <= nchunks; c++) {
+            if (warp == 1) {
+                if (lane == 0 && c < nchunks && !st) {
+                    uint32_t (*dstq)[3] = S.seq[c & 1];
+                    const uint32_t first = c * ZSK_SEQ_CHUNK;
+                    const uint32_t cnt = min(nseq - first, (uint32_t)ZSK_SEQ_CHUNK);
+                    uint32_t r0 = S.rep[0], r1 = S.rep[1], r2 = S.rep[2];
+                    for (uint32_t i = 0; i < cnt; i++) {
+                        const uint32_t el = S.fse_ll[sl], eo = S.fse_of[so], em = S.fse_ml[sm];
+                        const uint32_t lc = el & 0xff, oc = eo & 0xff, mc = em & 0xff;
+                        if (lc > 35 || oc > 31 || mc > 52) { st = ZSK_ST_TABLE; break; }
+                        const uint32_t ov = (1u << oc) + zsk_bits_read(b, oc);
+                        const uint32_t mlen = ZSK_ML_BASE[mc] + zsk_bits_read(b, ZSK_ML_BITS[mc]);
+                        const uint32_t llen = ZSK_LL_BASE[lc] + zsk_bits_read(b, ZSK_LL_BITS[lc]);
+                        if (first + i + 1 < nseq) {
+                            sl = (el >> 16) + zsk_bits_read(b, (el >> 8) & 0xff);
+                            sm = (em >> 16) + zsk_bits_read(b, (em >> 8) & 0xff);
+                            so = (eo >> 16) + zsk_bits_read(b, (eo >> 8) & 0xff);
+                        }
+                        if (b.pos < 0) { st = ZSK_ST_BITSTREAM; break; }
+                        uint32_t offset;
+                        if (ov > 3) { offset = ov - 3; r2 = r1; r1 = r0; r0 = offset; }
+                        else {
+                            const uint32_t idx = ov - 1 + (llen == 0);
+                            if (idx == 0) offset = r0;
+                            else {
+                                offset = idx == 1 ? r1 : idx == 2 ? r2 : r0 - 1;
+                                if (offset == 0) { st = ZSK_ST_OFFSET; break; }
+                                if (idx > 1) r2 = r1;
+                                r1 = r0;
+                                r0 = offset;
+                            }
+                        }
+                        dstq[i][0] = llen; dstq[i][1] = mlen; dstq[i][2] = offset;
+                    }
+                    S.rep[0] = r0; S.rep[1] = r1; S.rep[2] = r2;
+                    if (!st && c + 1 == nchunks && b.pos != 0) st = ZSK_ST_BITSTREAM;
+                }
+            } else if (c > 0) {
+                const uint32_t (*q)[3] = S.seq[(c - 1) & 1];
+                const uint32_t first = (c - 1) * ZSK_SEQ_CHUNK;
+                const uint32_t cnt = min(nseq - first, (uint32_t)ZSK_SEQ_CHUNK);
+                for (uint32_t i = 0; i < cnt; i++) {
+                    const uint32_t llen = q[i][0], mlen = q[i][1], offset = q[i][2];
+                    if (llen > regen - lpos) { st = ZSK_ST_FORMAT; break; }
+                    if (llen > cap - op || mlen > cap - op - llen) { st = ZSK_ST_DST; break; }
+                    if (llen) zsk_warp_literals(out + op, L, lpos, llen, lane);
+                    op += llen; lpos += llen;
+                    if (offset > op) { st = ZSK_ST_OFFSET; break; }
+                    __syncwarp();
+                    zsk_warp_match(out, op, offset, mlen, lane);
+                    __syncwarp();
+                    op += mlen;
+                }
+            }
+            if ((st = zsk_cta_status(S, st))) return st;
+        }
+    }
+    /* ---------------- literals after the last sequence (warp 0; op/lpos are only tracked there) */
+    if (warp == 0) {
+        const uint32_t rest = regen - lpos;
+        if (rest > cap - op) st = ZSK_ST_DST;
+        else if (rest) zsk_warp_literals(out + op, L, lpos, rest, lane);
+        if (lane == 0) S.op = op + rest;
+    }
+    if ((st = zsk_cta_status(S, st))) return st;
+    op = S.op;
+    if (op - *pop > ZSK_BLOCK_MAX) return ZSK_ST_FORMAT;
+    *pop = op;
+    return ZSK_ST_OK;
+}
+
+/* One complete zstd frame; all CTA threads call with identical arguments. */
+static __device__ int zsk_zstd_frame(zsk_zstd_smem &S, const uint8_t *__restrict__ src, uint32_t n, uint8_t *out, uint32_t cap,
+                                     uint32_t *produced, uint8_t *lit_scratch)
+{
+    const unsigned tid = threadIdx.x;
+    if (n < 6) return ZSK_ST_TRUNC;
+    if (zsk_rd32(src) != ZSK_ZSTD_MAGIC) return ZSK_ST_MAGIC;
+    const uint32_t fhd = ZSK_LDG(src + 4);
+    const uint32_t fcs_flag = fhd >> 6, ss = (fhd >> 5) & 1, cksum = (fhd >> 2) & 1, did = fhd & 3;
+    if (fhd & 0x08) return ZSK_ST_FORMAT;
+    uint32_t ip = 5;
+    if (!ss) ip += 1; /* window descriptor: the frame's own output is the window */
+    const uint32_t did_sz = did == 3 ? 4 : did;
+    if (did_sz) {
+        if (n - ip < did_sz) return ZSK_ST_TRUNC;
+        uint32_t id = 0;
+        for (uint32_t i = 0; i < did_sz; i++) id |= (uint32_t)ZSK_LDG(src + ip + i) << (8 * i);
+        if (id) return ZSK_ST_UNSUPPORTED;
+        ip += did_sz;
+    }
+    const uint32_t fcs_sz = fcs_flag == 0 ? ss : fcs_flag == 1 ? 2 : fcs_flag == 2 ? 4 : 8;
+    if (n < ip || n - ip < fcs_sz) return ZSK_ST_TRUNC;
+    uint64_t fcs = 0;
+    for (uint32_t i = 0; i < fcs_sz; i++) fcs |= (uint64_t)ZSK_LDG(src + ip + i) << (8 * i);
+    if (fcs_sz == 2) fcs += 256;
+    ip += fcs_sz;
+
+    if (tid == 0) {
+        S.rep[0] = 1; S.rep[1] = 4; S.rep[2] = 8;
+        S.log_ll = S.log_ml = S.log_of = S.log_huf = -1;
+        S.err = 0;
+    }
+    __syncthreads();
+    uint32_t op = 0;
+    for (;;) {
+        if (n - ip < 3) return ZSK_ST_TRUNC;
+        const uint32_t bh = zsk_rd24(src + ip);
+        ip += 3;
+        const uint32_t last = bh & 1, type = (bh >> 1) & 3, bsize = bh >> 3;
+        if (type == 0) {
+            if (bsize > n - ip) return ZSK_ST_TRUNC;
+            if (bsize > cap - op) return ZSK_ST_DST;
+            zsk_group_copy(out + op, src + ip, bsize, tid, blockDim.x);
+            op += bsize; ip += bsize;
+        } else if (type == 1) {
+            if (n - ip < 1) return ZSK_ST_TRUNC;
+            if (bsize > cap - op) return ZSK_ST_DST;
+            zsk_group_fill(out + op, ZSK_LDG(src + ip), bsize, tid, blockDim.x);
+            op += bsize; ip += 1;
+        } else if (type == 2) {
+            if (bsize > n - ip) return ZSK_ST_TRUNC;
+            if (bsize > ZSK_BLOCK_MAX) return ZSK_ST_FORMAT;
+            int st = zsk_zstd_block(S, src + ip, bsize, out, &op, cap, lit_scratch);
+            if (st) return st;
+            ip += bsize;
+        } else return ZSK_ST_FORMAT;
+        __syncthreads(); /* this block's output is visible to whoever reads it as match source next */
+        if (last) break;
+    }
+    if (cksum && n - ip < 4) return ZSK_ST_TRUNC;
+    if (fcs_sz && fcs != op) return ZSK_ST_FORMAT;
+    *produced = op;
+    return ZSK_ST_OK;
+}
+
+__global__ void __launch_bounds__(ZSK_ZSTD_CTA_THREADS) zsk_zstd_decode_kernel(zsk_decode_args a)
+{
+    __shared__ zsk_zstd_smem S;
+    uint8_t *lit_scratch = a.scratch + (size_t)blockIdx.x * ZSK_LIT_SCRATCH + 16;
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) S.job = atomicAdd(a.work_counter, 1u);
+        __syncthreads();
+        const uint32_t job = S.job;
+        if (job >= a.njobs) break;
+        const uint32_t f = a.frame_ids ? a.frame_ids[job] : a.first_frame + job;
+        const uint64_t c0 = a.c_off[f], c1 = a.c_off[f + 1], d0 = a.d_off[f], d1 = a.d_off[f + 1];
+        const uint8_t *src = a.comp + (c0 - a.comp_base);
+        uint8_t *out = a.dst + (a.dst_offs ? a.dst_offs[job] : d0 - a.dst_base);
+        const uint32_t cap = (uint32_t)(d1 - d0);
+        uint32_t produced = 0;
+        int st = zsk_zstd_frame(S, src, (uint32_t)(c1 - c0), out, cap, &produced, lit_scratch);
+        if (st == ZSK_ST_OK && produced != cap) st = ZSK_ST_SIZE;
+        if (threadIdx.x == 0) a.status[job] = st;
+    }
+}

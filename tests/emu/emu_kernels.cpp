@@ -1,0 +1,44 @@
+/* emu_kernels.cpp — TEST INFRASTRUCTURE ONLY: runs the product's kernel sources
+ * (libzseek_b200/csrc/zsk_*.cuh) on the lock-step CPU emulator of cuda_emu.h so tests can compare the
+ * kernel LOGIC with the oracle without a GPU.  Not part of libzseek_b200.so. */
+#define ZSK_EMU 1
+#include "cuda_emu.h"
+#include "../../libzseek_b200/csrc/zsk_lz4.cuh"
+#include "../../libzseek_b200/csrc/zsk_zstd.cuh"
+#include "../../libzseek_b200/csrc/zsk_seek.cuh"
+
+extern "C" {
+
+/* comp points at the byte with file offset comp_base; the caller guarantees >= 16 readable bytes
+ * before it and >= 64 after the last frame (same contract as the device buffers). */
+__attribute__((visibility("default")))
+void emu_decode(int codec, const uint8_t *comp, uint64_t comp_base, const uint64_t *c_off, const uint64_t *d_off,
+                const uint32_t *frame_ids, const uint64_t *dst_offs, uint8_t *dst, uint64_t dst_base,
+                uint32_t first_frame, uint32_t njobs, int32_t *status, uint32_t ctas)
+{
+    uint32_t counter = 0;
+    std::vector<uint8_t> scratch((size_t)ctas * ZSK_LIT_SCRATCH + 64);
+    zsk_decode_args a;
+    a.c_off = c_off; a.d_off = d_off; a.comp = comp; a.comp_base = comp_base; a.frame_ids = frame_ids;
+    a.dst_offs = dst_offs; a.dst = dst; a.dst_base = dst_base; a.first_frame = first_frame; a.njobs = njobs;
+    a.status = status; a.work_counter = &counter; a.scratch = scratch.data();
+    if (codec == 1) emu::launch(dim3(ctas), dim3(ZSK_LZ4_CTA_THREADS), 0, [&] { zsk_lz4_decode_kernel(a); });
+    else emu::launch(dim3(ctas), dim3(ZSK_ZSTD_CTA_THREADS), 0, [&] { zsk_zstd_decode_kernel(a); });
+}
+
+__attribute__((visibility("default")))
+void emu_lookup(const uint64_t *d_off, uint32_t nframes, const uint64_t *offsets, const uint64_t *counts,
+                uint64_t fixed_count, uint32_t n, int32_t *frame, uint32_t *inframe, uint32_t *nbytes, uint32_t *touched)
+{
+    zsk_lookup_args a{d_off, nframes, offsets, counts, fixed_count, n, frame, inframe, nbytes, touched};
+    emu::launch(dim3(2), dim3(256), 0, [&] { zsk_lookup_kernel(a); });
+}
+
+__attribute__((visibility("default")))
+void emu_gather(const int32_t *frame, const uint32_t *inframe, const uint32_t *nbytes, const int64_t *frame_src,
+                const uint8_t *src_base, uint8_t *dst, const uint64_t *dst_offs, uint64_t dst_stride, uint32_t n)
+{
+    zsk_gather_args a{frame, inframe, nbytes, frame_src, src_base, dst, dst_offs, dst_stride, n};
+    emu::launch(dim3(2), dim3(256), 0, [&] { zsk_gather_kernel(a); });
+}
+}

@@ -1,0 +1,40 @@
+"""ctypes wrapper of the kernel-logic emulator (tests/emu, TEST INFRASTRUCTURE ONLY)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+EMU_DIR = os.path.join(HERE, "emu")
+EMU_SO = os.path.join(EMU_DIR, "libzsk_emu.so")
+FRONT_PAD, BACK_PAD = 16, 64
+
+
+def lib():
+    subprocess.run(["make", "-C", EMU_DIR, "-s"], check=True)
+    L = C.CDLL(EMU_SO)
+    L.emu_decode.argtypes = [C.c_int, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                             C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32]
+    L.emu_lookup.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p,
+                             C.c_void_p, C.c_void_p, C.c_void_p]
+    L.emu_gather.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                             C.c_uint64, C.c_uint32]
+    return L
+
+
+def decode_all(L, image: bytes, codec: int, c_off: np.ndarray, d_off: np.ndarray, ctas: int = 3):
+    """Whole-file decode with the emulated K2/K3; returns (decoded bytes, status array)."""
+    n = len(c_off) - 1
+    payload = int(c_off[-1])
+    comp = np.zeros(FRONT_PAD + payload + BACK_PAD, dtype=np.uint8)
+    comp[FRONT_PAD:FRONT_PAD + payload] = np.frombuffer(image, dtype=np.uint8, count=payload)
+    total = int(d_off[-1])
+    dst = np.full(total + 64, 0xEE, dtype=np.uint8)
+    status = np.full(max(n, 1), -1, dtype=np.int32)
+    c_off = np.ascontiguousarray(c_off, dtype=np.uint64)
+    d_off = np.ascontiguousarray(d_off, dtype=np.uint64)
+    L.emu_decode(codec, comp.ctypes.data + FRONT_PAD, 0, c_off.ctypes.data, d_off.ctypes.data, None, None,
+                 dst.ctypes.data, 0, 0, n, status.ctypes.data, ctas)
+    assert (dst[total:] == 0xEE).all(), "emulated kernel wrote past the end of the output"
+    return dst[:total], status[:n]

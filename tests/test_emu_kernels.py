@@ -1,0 +1,83 @@
+"""Kernel LOGIC check without a GPU: the product's kernel sources (libzseek_b200/csrc/zsk_*.cuh) are
+compiled for the host against tests/emu/cuda_emu.h (every CUDA thread a fiber, warp collectives and
+barriers as rendezvous) and compared with the oracle.  Small inputs only — the emulator is slow.
+This is test infrastructure; the shipped library has no host decode path."""
+import hashlib
+
+import numpy as np
+import pytest
+
+import emu_api
+from oracle.pyapi import OraclePort
+
+EMU_CASES = ["tiny_zstd", "tiny_lz4", "zsyn_lz4_64k", "zsyn_lz4_256k_linked", "zsyn_zstd3_128k", "zsyn_zstd19_256k",
+             "zsyn_zstd3_mt", "mix_lz4", "mix_zstd3", "mix_zstd19"]
+
+
+@pytest.fixture(scope="module")
+def emu():
+    return emu_api.lib()
+
+
+@pytest.mark.parametrize("name", EMU_CASES)
+def test_emulated_decode_matches_reference_output(emu, golden, name):
+    cases, _ = golden
+    c = cases[name]
+    with OraclePort(c["image"]) as op:
+        out, status = emu_api.decode_all(emu, c["image"], op.codec, op.c_off, op.d_off, ctas=2)
+    assert (status == 0).all(), status
+    assert hashlib.sha256(out.tobytes()).hexdigest() == c["input_sha256"]
+
+
+def test_emulated_decode_flags_corrupt_frames(emu, golden):
+    """Truncation and bit flips must end in a non-zero status, never a hang or an out-of-bounds write."""
+    cases, _ = golden
+    for name in ("zsyn_lz4_64k", "zsyn_zstd3_128k"):
+        c = cases[name]
+        with OraclePort(c["image"]) as op:
+            img = bytearray(c["image"])
+            c0, c1 = int(op.c_off[1]), int(op.c_off[2])
+            for k in range(c0 + 20, c1, 997):  # sprinkle corruption over frame 1 only
+                img[k] ^= 0x55
+            out, status = emu_api.decode_all(emu, bytes(img), op.codec, op.c_off, op.d_off, ctas=2)
+            good = op.decode_all()
+        assert status[0] == 0 and (status[2:] == 0).all()
+        d0, d1 = int(op.d_off[1]), int(op.d_off[2])
+        assert (out[:d0] == good[:d0]).all() and (out[d1:] == good[d1:]).all()
+        # either the frame was rejected or (vanishingly unlikely) it decoded to other bytes of the right size
+        assert status[1] != 0 or not (out[d0:d1] == good[d0:d1]).all()
+
+
+def test_emulated_lookup_and_gather(emu, golden):
+    cases, _ = golden
+    c = cases["mix_zstd3"]
+    with OraclePort(c["image"]) as op:
+        decoded = op.decode_all()
+        d_off = np.ascontiguousarray(op.d_off, dtype=np.uint64)
+        n_frames = op.frames
+        rng = np.random.Generator(np.random.PCG64(3))
+        offsets = np.concatenate([rng.integers(0, op.size + 100, 500), d_off.astype(np.int64), d_off.astype(np.int64)[1:] - 1,
+                                  [op.size, op.size + 10 ** 9]]).astype(np.uint64)
+        counts = rng.choice([0, 1, 100, 4096, 70000], offsets.size).astype(np.uint64)
+        n = offsets.size
+        frame = np.zeros(n, np.int32)
+        inframe = np.zeros(n, np.uint32)
+        nbytes = np.zeros(n, np.uint32)
+        touched = np.zeros(n_frames + 1, np.uint32)
+        emu.emu_lookup(d_off.ctypes.data, n_frames, offsets.ctypes.data, counts.ctypes.data, 0, n, frame.ctypes.data,
+                       inframe.ctypes.data, nbytes.ctypes.data, touched.ctypes.data)
+        for i in range(n):
+            assert frame[i] == op.offset_to_frame(int(offsets[i]))
+            r, b = op.pread(int(counts[i]), int(offsets[i]))
+            assert nbytes[i] == r
+        # gather out of a "cache" that simply holds the whole decoded file
+        stride = 70000
+        src = np.zeros(16 + decoded.size + 64, np.uint8)
+        src[16:16 + decoded.size] = decoded
+        frame_src = d_off[:-1].astype(np.int64)
+        dst = np.zeros(n * stride + 64, np.uint8)
+        emu.emu_gather(frame.ctypes.data, inframe.ctypes.data, nbytes.ctypes.data, frame_src.ctypes.data,
+                       src.ctypes.data + 16, dst.ctypes.data, None, stride, n)
+        for i in range(n):
+            o, k = int(offsets[i]), int(nbytes[i])
+            assert (dst[i * stride:i * stride + k] == decoded[o:o + k]).all()
