@@ -69,6 +69,14 @@ ZSEEK_EXPORT ssize_t zseek_b200_pread_batch(zseek_reader_t *reader, size_t n, co
                                             const uint64_t *dst_offs, uint64_t dst_stride, int64_t *results,
                                             void *call_data, char errbuf[ZSEEK_ERRBUF_SIZE]);
 
+/* Forgets the HBM-resident compressed image (the next read pulls its frames again). */
+ZSEEK_EXPORT void zseek_b200_unload(zseek_reader_t *reader);
+
+/* Device-side stopwatch on the stream the kernels are launched on (CUDA events): start records an
+ * event, stop records a second one, waits for it and returns the milliseconds in between (<0 on error). */
+ZSEEK_EXPORT bool zseek_b200_timer_start(zseek_reader_t *reader);
+ZSEEK_EXPORT double zseek_b200_timer_stop(zseek_reader_t *reader);
+
 /* Drops every decoded frame from the HBM cache (benchmarks use it to time cold batches). */
 ZSEEK_EXPORT void zseek_b200_cache_clear(zseek_reader_t *reader);
 

@@ -1139,6 +1139,26 @@ void zseek_b200_cache_clear(zseek_reader_t *r)
     pthread_mutex_unlock(&r->lock);
 }
 
+void zseek_b200_unload(zseek_reader_t *r)
+{
+    if (!r)
+        return;
+    pthread_mutex_lock(&r->lock);
+    zsk_cuda_stream_sync(r->cx, ZSK_STREAM_COMPUTE);
+    r->res_lo = r->res_hi = 0;
+    pthread_mutex_unlock(&r->lock);
+}
+
+bool zseek_b200_timer_start(zseek_reader_t *r) { return r && zsk_cuda_timer_start(r->cx, ZSK_STREAM_COMPUTE) == 0; }
+
+double zseek_b200_timer_stop(zseek_reader_t *r)
+{
+    float ms = -1.0f;
+    if (!r || zsk_cuda_timer_stop(r->cx, ZSK_STREAM_COMPUTE, &ms))
+        return -1.0;
+    return ms;
+}
+
 unsigned long long zseek_b200_launch_count(zseek_reader_t *r) { return r ? zsk_cuda_launch_count(r->cx) : 0; }
 
 double zseek_b200_last_decode_ms(zseek_reader_t *r)

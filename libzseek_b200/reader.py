@@ -79,6 +79,12 @@ def load_library():
     L.zseek_b200_pread_batch.argtypes = [vp, sz, vp, vp, C.c_uint64, vp, vp, C.c_uint64, vp, vp, cp]
     L.zseek_b200_cache_clear.restype = None
     L.zseek_b200_cache_clear.argtypes = [vp]
+    L.zseek_b200_unload.restype = None
+    L.zseek_b200_unload.argtypes = [vp]
+    L.zseek_b200_timer_start.restype = C.c_bool
+    L.zseek_b200_timer_start.argtypes = [vp]
+    L.zseek_b200_timer_stop.restype = C.c_double
+    L.zseek_b200_timer_stop.argtypes = [vp]
     L.zseek_b200_launch_count.restype = C.c_ulonglong
     L.zseek_b200_launch_count.argtypes = [vp]
     L.zseek_b200_last_decode_ms.restype = C.c_double
@@ -122,10 +128,14 @@ class Reader:
                 raise ZseekError(f"cannot open {path}")
             h = self.L.zseek_reader_open(self._file, cache_size, None, self.err)
         elif image is not None:
-            arr = np.frombuffer(image, dtype=np.uint8) if not isinstance(image, np.ndarray) else image
-            arr = np.ascontiguousarray(arr)
-            self._keep.append(arr)
-            h = self.L.zseek_b200_reader_open_mem(arr.ctypes.data, arr.size, cache_size, self.err)
+            if hasattr(image, "data_ptr"):  # torch CPU tensor (e.g. pinned memory)
+                self._keep.append(image)
+                h = self.L.zseek_b200_reader_open_mem(image.data_ptr(), image.numel(), cache_size, self.err)
+            else:
+                arr = np.frombuffer(image, dtype=np.uint8) if not isinstance(image, np.ndarray) else image
+                arr = np.ascontiguousarray(arr)
+                self._keep.append(arr)
+                h = self.L.zseek_b200_reader_open_mem(arr.ctypes.data, arr.size, cache_size, self.err)
         elif pread is not None and fsize is not None:
             def _pread(data, size, offset, user, call):
                 try:
@@ -255,6 +265,19 @@ class Reader:
 
     def cache_clear(self):
         self.L.zseek_b200_cache_clear(self.h)
+
+    def unload(self):
+        self.L.zseek_b200_unload(self.h)
+
+    def timer_start(self):
+        if not self.L.zseek_b200_timer_start(self.h):
+            raise ZseekError("timer_start failed")
+
+    def timer_stop(self) -> float:
+        ms = float(self.L.zseek_b200_timer_stop(self.h))
+        if ms < 0:
+            raise ZseekError("timer_stop failed")
+        return ms
 
     @property
     def launch_count(self) -> int:

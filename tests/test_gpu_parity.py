@@ -1,0 +1,241 @@
+"""Parity tests proper: the CUDA path, called through the C-ABI library exactly as a libzseek caller
+would call it, against (a) the committed golden vectors = outputs of the reference itself, (b) the
+CPU oracle on freshly written files, (c) size-independent properties at larger sizes.
+Bar: bit-exact (integer/byte work)."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, golden_case_names, sha16
+from oracle.pyapi import LZ4, ZSTD, OraclePort, RefReader, have_reference
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+    assert torch.cuda.is_available(), "these tests need a CUDA device"
+    return torch
+
+
+# --------------------------------------------------------------------------- golden vectors
+@pytest.mark.parametrize("cache_size", [0, 1, 4])
+@pytest.mark.parametrize("name", golden_case_names())
+def test_pread_matches_reference_golden(lib, golden, name, cache_size, torch_cuda):
+    cases, _ = golden
+    c = cases[name]
+    with lib.Reader(image=c["image"], cache_size=cache_size) as rd:
+        st = rd.stats()
+        assert (st.frames, st.decompressed_size, st.seek_table_memory) == (c["frames"], c["input_len"], c["seek_table_memory"])
+        for off, cnt, ret, digest in c["reads"]:
+            r, b = rd.pread(cnt, off)
+            assert r == ret, (off, cnt)
+            assert sha16(b) == digest, (off, cnt)
+        whole = lib.pread_full(rd, c["input_len"] + 10, 0)
+        assert hashlib.sha256(whole).hexdigest() == c["input_sha256"]
+
+
+@pytest.mark.parametrize("name", ["zsyn_lz4_4k_chunks", "mix_zstd19"])
+def test_example_scan_4k_cache1(lib, golden, name, torch_cuda):
+    """reference test/example.c:36-87: open with cache_size 1 over a FILE*, scan with 4 KiB preads looping on
+    short reads, compare every chunk."""
+    cases, _ = golden
+    c = cases[name]
+    with OraclePort(c["image"]) as op:
+        want = op.decode_all().tobytes()
+    with lib.Reader(path=os.path.join(GOLDEN, name + ".zsk"), cache_size=1) as rd:
+        off = 0
+        while off < len(want):
+            chunk = lib.pread_full(rd, min(4096, len(want) - off), off)
+            assert chunk == want[off:off + 4096]
+            off += len(chunk)
+        assert rd.pread(4096, off) == (0, b"")
+
+
+def test_zseek_read_cursor(lib, golden, torch_cuda):
+    cases, _ = golden
+    c = cases["mix_lz4"]
+    with OraclePort(c["image"]) as op:
+        want = op.decode_all().tobytes()
+    with lib.Reader(image=c["image"], cache_size=2) as rd:
+        got = bytearray()
+        while True:
+            r, b = rd.read(7001)
+            if r == 0:
+                break
+            got += b
+        assert bytes(got) == want
+
+
+def test_python_callbacks_reader(lib, golden, torch_cuda):
+    """zseek_reader_open_full with user callbacks (reference src/zseek.h:88-116), short read only at EOF."""
+    cases, _ = golden
+    img = cases["zsyn_zstd3_128k"]["image"]
+    calls = []
+
+    def pread(size, offset):
+        calls.append((size, offset))
+        return img[offset:offset + size]
+    with lib.Reader(pread=pread, fsize=lambda: len(img), cache_size=0) as rd:
+        r, b = rd.pread(1000, 200000)
+        with OraclePort(img) as op:
+            assert (r, b) == op.pread(1000, 200000)
+    assert calls[0] == (4, 0)  # magic sniff first, like the reference
+
+
+def test_io_errors_surface_like_the_reference(lib, golden, torch_cuda):
+    cases, _ = golden
+    img = cases["zsyn_lz4_64k"]["image"]
+    state = {"fail": False}
+
+    def pread(size, offset):
+        if state["fail"] and offset < 100000:
+            return None  # <0
+        return img[offset:offset + size]
+    with lib.Reader(pread=pread, fsize=lambda: len(img), cache_size=0) as rd:
+        state["fail"] = True
+        with pytest.raises(lib.ZseekError) as e:
+            rd.pread(10, 5)
+        assert str(e.value) == "read file failed"
+    short = img[:50000] + bytes(len(img) - 50000)
+
+    def pread2(size, offset):
+        if offset + size <= 60000 and offset < 50000 and size > 16:
+            return img[offset:offset + size][:size // 2]  # short in the middle of the file
+        return img[offset:offset + size]
+    with lib.Reader(pread=pread2, fsize=lambda: len(img), cache_size=0) as rd:
+        with pytest.raises(lib.ZseekError) as e:
+            rd.pread(10, 5)
+        assert str(e.value) == "unexpected EOF"
+
+
+def test_corrupt_frame_fails_instead_of_hanging(lib, golden, torch_cuda):
+    """the reference can spin forever on a frame that yields fewer bytes than the seek table
+    claims; the replacement must return -1."""
+    cases, _ = golden
+    for name in ("zsyn_lz4_64k", "zsyn_zstd3_128k", "mix_zstd19"):
+        c = cases[name]
+        with OraclePort(c["image"]) as op:
+            good = op.decode_all()
+            img = bytearray(c["image"])
+            f = int(np.argmax(np.diff(op.c_off.astype(np.int64))[1:-1])) + 1  # a big frame that is neither first nor last
+            c0, c1 = int(op.c_off[f]), int(op.c_off[f + 1])
+            for k in range(c0 + 20, c1, 97):
+                img[k] ^= 0x55
+            d0, d1 = int(op.d_off[f]), int(op.d_off[f + 1])
+        with lib.Reader(image=bytes(img), cache_size=0) as rd:
+            assert rd.pread(100, 0)[1] == good[:100].tobytes()
+            try:
+                b = rd.read_range(d1 - d0, d0)   # either rejected, or decoded to different bytes of the claimed size
+                assert len(b) == d1 - d0 and b != good[d0:d1].tobytes()
+            except lib.ZseekError as e:
+                assert str(e).startswith("decompress frame")
+            assert rd.pread(100, d1 + 5)[1] == good[d1 + 5:d1 + 105].tobytes()
+
+
+# --------------------------------------------------------------------------- oracle on fresh files
+def fresh_files():
+    from datagen import refwriter, zsyn
+    data = zsyn.gen(6 << 20, seed=99)
+    yield "lz4_64k", data, refwriter.write(data, LZ4, 0, 65536)
+    yield "lz4_1m_linked", data, refwriter.write(data, LZ4, 0, 1 << 20, 4096)
+    yield "zstd3_256k", data, refwriter.write(data, ZSTD, 3, 262144)
+    yield "zstd19_1m", data[:3 << 20], refwriter.write(data[:3 << 20], ZSTD, 19, 1 << 20)
+    yield "zstd1_ragged", data, refwriter.write(data, ZSTD, 1, 100000, 4093)
+    yield "zstd_mt", data, refwriter.write(data, ZSTD, 3, 262144, 262144, 0, 2)
+
+
+@pytest.mark.skipif(not have_reference(), reason="oracle/_ref/libzseek_ref.so missing")
+def test_fresh_files_all_entry_points(lib, torch_cuda):
+    torch = torch_cuda
+    for name, data, image in fresh_files():
+        total = len(data)
+        ref = np.frombuffer(data, dtype=np.uint8)
+        with lib.Reader(image=image, cache_size=8) as rd, OraclePort(image) as op, RefReader(image) as rr:
+            assert op.decode_all().tobytes() == data
+            # (1) whole-file decode straight into device memory
+            dev = torch.empty(total + 64, dtype=torch.uint8, device="cuda")
+            dev.fill_(0xEE)
+            assert rd.decode_frames(0, rd.frames, dev) == total
+            assert torch.equal(dev[:total].cpu(), torch.from_numpy(ref.copy())), name
+            assert bool((dev[total:] == 0xEE).all()), "wrote past the end"
+            assert rd.launch_count >= 1 and rd.last_decode_ms > 0
+            # (2) zseek_pread with a DEVICE destination
+            rng = np.random.Generator(np.random.PCG64(5))
+            for _ in range(20):
+                off, cnt = int(rng.integers(0, total)), int(rng.choice([1, 4096, 300000]))
+                d = torch.zeros(cnt, dtype=torch.uint8, device="cuda")
+                r = rd.pread_into(d, cnt, off)
+                want = rr.pread(cnt, off)
+                assert r == want[0] and d[:r].cpu().numpy().tobytes() == want[1]
+            # (3) multi-frame range reads, host and device destinations
+            for off, cnt in [(0, total), (1, total), (70001, 1500000), (total - 5, 100), (total, 10), (123, 0)]:
+                want = data[off:off + cnt]
+                assert rd.read_range(cnt, off) == want, (name, off, cnt)
+                d = torch.zeros(max(cnt, 1), dtype=torch.uint8, device="cuda")
+                r = rd.read_range_into(d, cnt, off)
+                assert r == len(want) and d[:r].cpu().numpy().tobytes() == want
+            # (4) batch == loop of zseek_pread (reference), host and device destinations
+            n = 3000
+            offs = rng.integers(0, total + 1000, n).astype(np.uint64)
+            offs[:op.frames] = op.d_off[1:] - 1  # boundary straddlers
+            cnts = rng.choice([0, 1, 100, 4096, 8192], n).astype(np.uint64)
+            stride = 8192
+            hdst = np.zeros(n * stride, dtype=np.uint8)
+            res = rd.pread_batch(offs, counts=cnts, dst=hdst, dst_stride=stride)
+            ddst = torch.zeros(n * stride, dtype=torch.uint8, device="cuda")
+            rd.cache_clear()
+            res2 = rd.pread_batch(offs, fixed_count=4096, dst=ddst, dst_stride=stride)
+            dd = ddst.cpu().numpy()
+            for i in range(n):
+                r, b = rr.pread(int(cnts[i]), int(offs[i]))
+                assert res[i] == r and hdst[i * stride:i * stride + r].tobytes() == b, (name, i)
+                r, b = rr.pread(4096, int(offs[i]))
+                assert res2[i] == r and dd[i * stride:i * stride + r].tobytes() == b, (name, i)
+
+
+def test_shard_restricts_frames(lib, golden, torch_cuda):
+    cases, _ = golden
+    c = cases["mix_zstd3"]
+    with lib.Reader(image=c["image"]) as rd, OraclePort(c["image"]) as op:
+        lo, hi = rd.set_shard(1, 2)
+        assert (lo, hi) == (op.frames // 2, op.frames)
+        good = op.decode_all()
+        o = int(op.d_off[lo])
+        assert rd.pread(100, o)[1] == good[o:o + 100].tobytes()
+        with pytest.raises(lib.ZseekError) as e:
+            rd.pread(100, 0)
+        assert "shard" in str(e.value)
+
+
+# --------------------------------------------------------------------------- properties at size
+@pytest.mark.skipif(not have_reference(), reason="oracle/_ref/libzseek_ref.so missing")
+@pytest.mark.parametrize("codec,level,frame", [(LZ4, 0, 65536), (ZSTD, 3, 262144)])
+def test_round_trip_256mib(lib, codec, level, frame, torch_cuda):
+    """Size-independent property (the reference's own check, test/example.c:82-86): decode(write(x)) == x,
+    at 256 MiB built by tile-and-replicate; compared on the device, plus random 4 KiB probes vs the source."""
+    torch = torch_cuda
+    from datagen import refwriter, zsyn
+    tile = zsyn.gen_parallel(32 << 20)
+    image = refwriter.replicate(refwriter.write_parallel(tile, codec, level, frame), 8)
+    total = len(tile) * 8
+    with lib.Reader(image=image, cache_size=64) as rd:
+        assert rd.size == total
+        dev = torch.empty(total, dtype=torch.uint8, device="cuda")
+        assert rd.decode_frames(0, rd.frames, dev) == total
+        t = torch.from_numpy(np.frombuffer(tile, dtype=np.uint8).copy()).cuda()
+        assert bool((dev.view(8, -1) == t).all())
+        rng = np.random.Generator(np.random.PCG64(11))
+        offs = rng.integers(0, total - 4096, 20000).astype(np.uint64)
+        out = torch.zeros(20000 * 4096, dtype=torch.uint8, device="cuda")
+        res = rd.pread_batch(offs, fixed_count=4096, dst=out, dst_stride=4096)
+        # a request returns MIN(4096, frame_end - offset): check exactly those bytes
+        src = np.frombuffer(tile, dtype=np.uint8)
+        o = out.cpu().numpy().reshape(20000, 4096)
+        for i in range(0, 20000, 37):
+            k, a = int(res[i]), int(offs[i]) % len(tile)
+            assert k == min(4096, frame - int(offs[i]) % frame)
+            assert (o[i, :k] == src[a:a + k]).all() if a + k <= len(tile) else True
