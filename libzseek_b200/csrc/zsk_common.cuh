@@ -101,29 +101,37 @@ static __device__ __forceinline__ void zsk_group_fill(uint8_t *dst, uint8_t v, u
 }
 
 /* ------------------------------------------------------------------------------------------
- * LZ77 match copy by one warp: dst[op .. op+ml) = dst[op-off ..), byte-serial semantics when the
- * regions overlap (off < ml replicates the pattern).  All lanes call with identical arguments.
- * The caller has made earlier stores visible (__syncwarp) and must __syncwarp afterwards.
+ * LZ77 match copy by a lane group of G lanes (G = 32: a warp, G = 8: a quarter warp):
+ * out[op .. op+ml) = out[op-off ..), byte-serial semantics when the regions overlap (off < ml
+ * replicates the pattern).  All lanes of the group call with identical arguments; gl = lane index
+ * inside the group, gmask = the group's lanes.  The caller has made earlier stores visible
+ * (__syncwarp(gmask)) and must sync again afterwards.
  * ------------------------------------------------------------------------------------------ */
-static __device__ __forceinline__ void zsk_warp_match(uint8_t *out, uint32_t op, uint32_t off, uint32_t ml, unsigned lane)
+template <unsigned G>
+static __device__ __forceinline__ void zsk_group_match(uint8_t *out, uint32_t op, uint32_t off, uint32_t ml, unsigned gl, unsigned gmask)
 {
-    if (off >= 32 || off >= ml) {
-        /* every 32-byte slice reads only bytes written before the slice started */
+    if (off >= G || off >= ml) {
+        /* every G-byte slice reads only bytes written before the slice started */
         const bool overlap = off < ml;
-        for (uint32_t base = 0; base < ml; base += 32) {
-            uint32_t i = base + lane;
+        for (uint32_t base = 0; base < ml; base += G) {
+            uint32_t i = base + gl;
             if (i < ml) out[op + i] = out[op + i - off];
-            if (overlap) __syncwarp();
+            if (overlap) __syncwarp(gmask);
         }
     } else {
         /* short period: every byte is a copy of one of the `off` bytes before op */
         const uint8_t *pat = out + op - off;
-        uint32_t r = lane % off;
-        const uint32_t step = 32 % off;
-        for (uint32_t i = lane; i < ml; i += 32) {
+        uint32_t r = gl % off;
+        const uint32_t step = G % off;
+        for (uint32_t i = gl; i < ml; i += G) {
             out[op + i] = pat[r];
             r += step;
             if (r >= off) r -= off;
         }
     }
+}
+
+static __device__ __forceinline__ void zsk_warp_match(uint8_t *out, uint32_t op, uint32_t off, uint32_t ml, unsigned lane)
+{
+    zsk_group_match<32>(out, op, off, ml, lane, ZSK_FULL);
 }

@@ -29,6 +29,7 @@ struct zsk_cuda_ctx {
     unsigned counter_next;
     uint8_t *scratch;                    /* zstd literal scratch for zstd_ctas CTAs */
     int zstd_ctas, lz4_ctas;
+    int lz4_group;                       /* lanes per LZ4 frame (ZSEEK_B200_LZ4_GROUP: 4, 8, 16 or 32) */
     unsigned long long launches;
     char err[160];
 };
@@ -98,7 +99,12 @@ int zsk_cuda_ctx_create(int device, zsk_cuda_ctx **out, char *err, size_t errlen
     CK0(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, zsk_zstd_decode_kernel, ZSK_ZSTD_CTA_THREADS, 0));
     if (per_sm < 1) per_sm = 1;
     cx->zstd_ctas = per_sm * cx->sm_count;
-    CK0(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, zsk_lz4_decode_kernel, ZSK_LZ4_CTA_THREADS, 0));
+    cx->lz4_group = 0;                   /* 0 = lock-step kernel (8 lanes per frame) */
+    if (const char *g = getenv("ZSEEK_B200_LZ4_GROUP")) {
+        int v = atoi(g);
+        if (v == 4 || v == 8 || v == 16 || v == 32) cx->lz4_group = v;   /* plain per-group variants, for A/B runs */
+    }
+    CK0(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, zsk_lz4_decode_lockstep_kernel, ZSK_LZ4_CTA_THREADS, 0));
     if (per_sm < 1) per_sm = 1;
     cx->lz4_ctas = per_sm * cx->sm_count;
     CK0(cudaMalloc((void **)&cx->scratch, (size_t)cx->zstd_ctas * ZSK_LIT_SCRATCH + ZSK_PAD_BACK));
@@ -242,10 +248,16 @@ int zsk_cuda_launch_decode(zsk_cuda_ctx *cx, int codec, const zsk_decode_args *a
     cudaStream_t s = cx->streams[stream];
     CK(cx, cudaEventRecord(cx->k0, s));
     if (codec == ZSK_CODEC_LZ4) {
-        const unsigned warps_per_cta = ZSK_LZ4_CTA_THREADS / 32;
-        unsigned ctas = (a.njobs + warps_per_cta - 1) / warps_per_cta;
+        const unsigned frames_per_cta = ZSK_LZ4_CTA_THREADS / (unsigned)(cx->lz4_group ? cx->lz4_group : 8);
+        unsigned ctas = (a.njobs + frames_per_cta - 1) / frames_per_cta;
         if (ctas > (unsigned)cx->lz4_ctas) ctas = (unsigned)cx->lz4_ctas;
-        zsk_lz4_decode_kernel<<<ctas, ZSK_LZ4_CTA_THREADS, 0, s>>>(a);
+        switch (cx->lz4_group) {
+        case 4: zsk_lz4_decode_kernel<4><<<ctas, ZSK_LZ4_CTA_THREADS, 0, s>>>(a); break;
+        case 16: zsk_lz4_decode_kernel<16><<<ctas, ZSK_LZ4_CTA_THREADS, 0, s>>>(a); break;
+        case 32: zsk_lz4_decode_kernel<32><<<ctas, ZSK_LZ4_CTA_THREADS, 0, s>>>(a); break;
+        case 8: zsk_lz4_decode_kernel<8><<<ctas, ZSK_LZ4_CTA_THREADS, 0, s>>>(a); break;
+        default: zsk_lz4_decode_lockstep_kernel<<<ctas, ZSK_LZ4_CTA_THREADS, 0, s>>>(a); break;
+        }
     } else if (codec == ZSK_CODEC_ZSTD) {
         unsigned ctas = a.njobs < (unsigned)cx->zstd_ctas ? a.njobs : (unsigned)cx->zstd_ctas;
         zsk_zstd_decode_kernel<<<ctas, ZSK_ZSTD_CTA_THREADS, 0, s>>>(a);

@@ -1,0 +1,40 @@
+"""Small driver for profiling one decode kernel under ncu (inputs: reference writer over a zsyn-v1 tile).
+
+    python tools/prof_decode.py lz4|zstd3|zstd19 [size_mib] [iters]
+"""
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    import torch
+    import libzseek_b200 as z
+    from datagen import refwriter, zsyn
+    kind = sys.argv[1] if len(sys.argv) > 1 else "lz4"
+    size = (int(sys.argv[2]) if len(sys.argv) > 2 else 256) << 20
+    iters = int(sys.argv[3]) if len(sys.argv) > 3 else 3
+    tile = zsyn.gen_parallel(min(size, 64 << 20))
+    codec, level, frame = {"lz4": (1, 0, 65536), "zstd3": (0, 3, 262144), "zstd19": (0, 19, 1 << 20), "lz4_1m": (1, 0, 1 << 20)}[kind]
+    one = refwriter.write_parallel(tile, codec, level, frame, piece_frames=max(1, (4 << 20) // frame))
+    image = refwriter.replicate(one, max(1, size // len(tile)))
+    with z.Reader(image=image) as rd:
+        out = torch.empty(rd.size + 64, dtype=torch.uint8, device="cuda")
+        rd.load(0, rd.frames)
+        for i in range(iters):
+            rd.decode_frames(0, rd.frames, out)
+            ms = rd.last_decode_ms
+            print(f"{kind}: {rd.size / 2**20:.0f} MiB, {rd.frames} frames, C={int(rd.c_off[-1])} kernel {ms:.3f} ms -> {rd.size / ms / 1e6:.1f} GB/s decompressed, "
+                  f"{(rd.size + int(rd.c_off[-1])) / ms / 1e6:.1f} GB/s algorithmic", flush=True)
+        ref = np.frombuffer(tile, dtype=np.uint8)
+        got = out[:len(tile)].cpu().numpy()
+        assert (got == ref).all(), "decode mismatch"
+
+
+if __name__ == "__main__":
+    main()
