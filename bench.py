@@ -112,36 +112,60 @@ def cleanup_inputs(cache, rank):
 
 # ----------------------------------------------------------------------------- clocks
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi sampled every 20 ms from before the warm-up; only samples whose timestamp falls inside the
+    timed region (mark_start .. mark_end) are summarised."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, device):
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.t0 = self.t1 = None
         try:
-            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                                        "-i", str(device)], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
 
+    def mark_start(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
+
     def stop(self):
+        import datetime
         if self.p is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.05)
         self.p.terminate()
         try:
             self.p.wait(5)
         except Exception:
             self.p.kill()
         self.f.flush()
-        rows = [r.split(",") for r in open(self.f.name).read().strip().splitlines() if r.count(",") >= 8]
+        rows = []
+        for line in open(self.f.name).read().strip().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 8:
+                continue
+            try:
+                ts = datetime.datetime.strptime(c[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                rows.append((ts, float(c[1]), float(c[2]), float(c[3]), c[4:8]))
+            except ValueError:
+                continue
         os.unlink(self.f.name)
         if not rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        sm = sorted(float(r[1]) for r in rows)
-        power = max(float(r[3]) for r in rows if r[3].strip().replace(".", "").isdigit() or True)
+        inside = [r for r in rows if self.t0 is not None and self.t0 - 0.02 <= r[0] <= self.t1 + 0.02]
+        scope = "timed region"
+        if not inside:  # region shorter than the sampling period: fall back to the busiest samples of the run
+            inside = sorted(rows, key=lambda r: -r[3])[:max(1, len(rows) // 4)]
+            scope = "highest-power quarter of the run (timed region shorter than one sample)"
+        sm = sorted(r[1] for r in inside)
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for j, n in enumerate(names) if any("Active" in r[5 + j] and "Not" not in r[5 + j] for r in rows)]
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][2]), "power_w_max": power, "samples": len(rows),
-                "reasons": reasons}
+        reasons = [n for j, n in enumerate(names) if any(r[4][j].startswith("Active") for r in inside)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": inside[0][2], "power_w_max": max(r[3] for r in inside),
+                "samples": len(inside), "scope": scope, "reasons": reasons}
 
 
 # ----------------------------------------------------------------------------- CPU (reference) legs
@@ -206,12 +230,14 @@ def run_b200(args, rank, world):
         rd = z.Reader(image=pinned, cache_size=0)
         C = int(rd.c_off[-1])
         dev_out = torch.empty(total + 64, dtype=torch.uint8, device="cuda")
+        sampler = ClockSampler(local) if (name == "lz4" and rank == 0) else None
         rd.load(0, rd.frames)                                       # compressed image resident in HBM
         for _ in range(args.warmup):
             rd.decode_frames(0, rd.frames, dev_out)
         barrier()
-        sampler = ClockSampler(local) if (name == "lz4" and rank == 0) else None
         l0 = rd.launch_count
+        if sampler:
+            sampler.mark_start()
         rd.timer_start()
         wall0 = time.perf_counter()
         kernel_ms = 0.0
@@ -222,6 +248,7 @@ def run_b200(args, rank, world):
         barrier()
         wall = time.perf_counter() - wall0
         if sampler:
+            sampler.mark_end()
             clocks = sampler.stop()
         launches = rd.launch_count - l0
         dev_ms = max_over_ranks(dev_ms)

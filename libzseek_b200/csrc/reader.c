@@ -67,6 +67,7 @@ struct zseek_reader {
     /* pinned host staging */
     uint8_t *h_stage; /* two halves */
     size_t stage_half;
+    int stage_next, stage_inflight;
     uint8_t *h_mirror; /* decoded bytes of frames [mir_lo, mir_hi) */
     size_t mirror_cap;
     uint64_t mir_lo, mir_hi;
@@ -103,6 +104,7 @@ struct zseek_reader {
     /* read-ahead */
     uint64_t ra_next;
     uint32_t ra_window, ra_max;
+    size_t chunk_bytes; /* decoded bytes per pipeline stage of host-destination range reads */
 };
 
 /* ------------------------------------------------------------------ errors (reference src/common.c:45-54) */
@@ -328,25 +330,10 @@ static void cache_clear(zseek_reader_t *r)
 }
 
 /* ------------------------------------------------------------------ compressed image residency */
-static bool ensure_resident(zseek_reader_t *r, uint64_t lo, uint64_t hi, void *call_data, char *errbuf)
+/* Queues the copy of file bytes [file_off, file_off + bytes) to device memory `dst` on the H2D
+ * stream: one DMA straight from the memory image, or pread-callback -> pinned staging halves -> DMA. */
+static bool h2d_range(zseek_reader_t *r, size_t file_off, size_t bytes, uint8_t *dst, void *call_data, char *errbuf)
 {
-    if (lo >= hi || (lo >= r->res_lo && hi <= r->res_hi))
-        return true;
-    size_t bytes = (size_t)(r->c_off[hi] - r->c_off[lo]);
-    size_t need = bytes + ZSK_PAD_FRONT + ZSK_PAD_BACK;
-    /* everything queued against the old image must have finished before it is replaced */
-    if (zsk_cuda_stream_sync(r->cx, ZSK_STREAM_COMPUTE)) return cuda_fail(r, errbuf, "synchronize");
-    if (need > r->g_comp_cap) {
-        zsk_cuda_free(r->cx, r->g_comp);
-        r->g_comp = NULL;
-        r->g_comp_cap = 0;
-        r->res_lo = r->res_hi = 0;
-        if (zsk_cuda_malloc(r->cx, (void **)&r->g_comp, need)) return cuda_fail(r, errbuf, "allocate device image");
-        r->g_comp_cap = need;
-    }
-    r->res_lo = r->res_hi = 0;
-    uint8_t *dst = r->g_comp + ZSK_PAD_FRONT;
-    size_t file_off = (size_t)r->c_off[lo];
     if (r->mem_image) {
         if (file_off + bytes > r->mem_size) {
             set_error(errbuf, "unexpected EOF");
@@ -354,32 +341,63 @@ static bool ensure_resident(zseek_reader_t *r, uint64_t lo, uint64_t hi, void *c
         }
         if (zsk_cuda_memcpy_async(r->cx, dst, r->mem_image + file_off, bytes, ZSK_H2D, ZSK_STREAM_H2D))
             return cuda_fail(r, errbuf, "copy image to device");
-    } else {
-        size_t done = 0;
-        int half = 0, inflight = 0;
-        while (done < bytes) {
-            size_t n = MIN(r->stage_half, bytes - done);
-            if (inflight == 2) { /* the half about to be refilled may still be in flight */
-                if (zsk_cuda_stream_sync(r->cx, ZSK_STREAM_H2D)) return cuda_fail(r, errbuf, "synchronize");
-                inflight = 0;
-            }
-            uint8_t *st = r->h_stage + (size_t)half * r->stage_half;
-            ssize_t got = r->user_file.pread(st, n, file_off + done, r->user_file.user_data, call_data);
-            if (got != (ssize_t)n) {
-                zsk_cuda_stream_sync(r->cx, ZSK_STREAM_H2D);
-                set_error(errbuf, got >= 0 ? "unexpected EOF" : "read file failed");
-                return false;
-            }
-            if (zsk_cuda_memcpy_async(r->cx, dst + done, st, n, ZSK_H2D, ZSK_STREAM_H2D))
-                return cuda_fail(r, errbuf, "copy frames to device");
-            done += n;
-            half ^= 1;
-            inflight++;
-        }
+        return true;
     }
+    size_t done = 0;
+    while (done < bytes) {
+        size_t n = MIN(r->stage_half, bytes - done);
+        if (r->stage_inflight == 2) { /* the half about to be refilled may still be in flight */
+            if (zsk_cuda_stream_sync(r->cx, ZSK_STREAM_H2D)) return cuda_fail(r, errbuf, "synchronize");
+            r->stage_inflight = 0;
+        }
+        uint8_t *st = r->h_stage + (size_t)r->stage_next * r->stage_half;
+        ssize_t got = r->user_file.pread(st, n, file_off + done, r->user_file.user_data, call_data);
+        if (got != (ssize_t)n) {
+            zsk_cuda_stream_sync(r->cx, ZSK_STREAM_H2D);
+            r->stage_inflight = 0;
+            set_error(errbuf, got >= 0 ? "unexpected EOF" : "read file failed");
+            return false;
+        }
+        if (zsk_cuda_memcpy_async(r->cx, dst + done, st, n, ZSK_H2D, ZSK_STREAM_H2D))
+            return cuda_fail(r, errbuf, "copy frames to device");
+        done += n;
+        r->stage_next ^= 1;
+        r->stage_inflight++;
+    }
+    return true;
+}
+
+/* (re)allocates the device image for frames [lo, hi) without filling it; residency is cleared */
+static bool alloc_image(zseek_reader_t *r, uint64_t lo, uint64_t hi, char *errbuf)
+{
+    size_t need = (size_t)(r->c_off[hi] - r->c_off[lo]) + ZSK_PAD_FRONT + ZSK_PAD_BACK;
+    /* everything queued against the old image must have finished before it is replaced */
+    if (zsk_cuda_stream_sync(r->cx, ZSK_STREAM_COMPUTE)) return cuda_fail(r, errbuf, "synchronize");
+    r->res_lo = r->res_hi = 0;
+    if (need > r->g_comp_cap) {
+        zsk_cuda_free(r->cx, r->g_comp);
+        r->g_comp = NULL;
+        r->g_comp_cap = 0;
+        if (zsk_cuda_malloc(r->cx, (void **)&r->g_comp, need)) return cuda_fail(r, errbuf, "allocate device image");
+        r->g_comp_cap = need;
+    }
+    return true;
+}
+
+static bool ensure_resident(zseek_reader_t *r, uint64_t lo, uint64_t hi, void *call_data, char *errbuf)
+{
+    if (lo >= hi || (lo >= r->res_lo && hi <= r->res_hi))
+        return true;
+    if (!alloc_image(r, lo, hi, errbuf))
+        return false;
+    if (!h2d_range(r, (size_t)r->c_off[lo], (size_t)(r->c_off[hi] - r->c_off[lo]), r->g_comp + ZSK_PAD_FRONT, call_data, errbuf))
+        return false;
     /* kernels queued later on the compute stream see the complete image */
     if (zsk_cuda_stream_wait(r->cx, ZSK_STREAM_COMPUTE, ZSK_STREAM_H2D)) return cuda_fail(r, errbuf, "order streams");
-    if (!r->mem_image && zsk_cuda_stream_sync(r->cx, ZSK_STREAM_H2D)) return cuda_fail(r, errbuf, "synchronize");
+    if (!r->mem_image) {
+        if (zsk_cuda_stream_sync(r->cx, ZSK_STREAM_H2D)) return cuda_fail(r, errbuf, "synchronize");
+        r->stage_inflight = 0;
+    }
     r->res_lo = lo;
     r->res_hi = hi;
     return true;
@@ -586,6 +604,7 @@ static zseek_reader_t *reader_open_common(zseek_reader_t *r, size_t cache_size, 
     if (r->stage_half < r->max_csize)
         r->stage_half = r->max_csize;
     r->mirror_cap = (size_t)r->ra_max * r->max_dsize;
+    r->chunk_bytes = env_size("ZSEEK_B200_CHUNK_MB", 512) << 20;
 
     r->slot_frame = malloc(r->nslots * sizeof(int32_t));
     r->lru_prev = malloc(r->nslots * sizeof(int32_t));
@@ -916,6 +935,143 @@ static bool ensure_out(zseek_reader_t *r, size_t n, char *errbuf)
     return true;
 }
 
+/* events of the host-destination pipeline */
+enum { EV_H2D0 = 0, EV_H2D1 = 1, EV_DEC0 = 2, EV_DEC1 = 3, EV_D2H0 = 4, EV_D2H1 = 5 };
+
+/*
+ * Whole frames [lo, hi) -> HOST memory `dst` as a three-stage pipeline over chunks of ~chunk_bytes:
+ *     H2D stream     : compressed bytes of chunk k+1 (pinned image / staged callback reads)
+ *     compute stream : decode kernel of chunk k into device staging half k&1
+ *     D2H stream     : decoded bytes of chunk k-1 to the caller's buffer
+ * The host only queues work; chunks are ordered by events, so PCIe runs in both directions while
+ * the kernel of the next chunk executes.
+ */
+static bool stream_frames_to_host(zseek_reader_t *r, uint64_t lo, uint64_t hi, uint8_t *dst, void *call_data, char *errbuf)
+{
+    const uint64_t nfr = hi - lo;
+    const bool resident = lo >= r->res_lo && hi <= r->res_hi;
+    size_t chunk = MAX(r->chunk_bytes, (size_t)r->max_dsize);
+    if (!ensure_jobs(r, (uint32_t)nfr, errbuf) || !ensure_out(r, 2 * chunk, errbuf))
+        return false;
+    if (!resident && !alloc_image(r, lo, hi, errbuf))
+        return false;
+    const uint64_t img_lo = resident ? r->res_lo : lo;
+    uint8_t *img = r->g_comp + ZSK_PAD_FRONT;
+    bool ok = true;
+    uint64_t a = lo, next_b = lo;
+    unsigned k = 0;
+    /* chunk k = frames [a, b): as many frames as fit `chunk` decoded bytes */
+#define CHUNK_END(from, to)                                                                             \
+    do {                                                                                                \
+        (to) = (from) + 1;                                                                              \
+        while ((to) < hi && r->d_off[(to) + 1] - r->d_off[(from)] <= chunk) (to)++;                     \
+    } while (0)
+    uint64_t b;
+    CHUNK_END(a, b);
+    if (!resident) {
+        ok = h2d_range(r, (size_t)r->c_off[a], (size_t)(r->c_off[b] - r->c_off[a]), img + (r->c_off[a] - r->c_off[img_lo]), call_data, errbuf) &&
+             (zsk_cuda_event_record(r->cx, EV_H2D0, ZSK_STREAM_H2D) == 0 || cuda_fail(r, errbuf, "order streams"));
+    }
+    while (ok && a < hi) {
+        const int half = (int)(k & 1);
+        if (b < hi && !resident) { /* prefetch the compressed bytes of chunk k+1 */
+            CHUNK_END(b, next_b);
+            ok = h2d_range(r, (size_t)r->c_off[b], (size_t)(r->c_off[next_b] - r->c_off[b]), img + (r->c_off[b] - r->c_off[img_lo]), call_data, errbuf) &&
+                 (zsk_cuda_event_record(r->cx, EV_H2D0 + (half ^ 1), ZSK_STREAM_H2D) == 0 || cuda_fail(r, errbuf, "order streams"));
+            if (!ok) break;
+        } else if (b < hi) {
+            CHUNK_END(b, next_b);
+        }
+        if (!resident && zsk_cuda_stream_wait_event(r->cx, ZSK_STREAM_COMPUTE, EV_H2D0 + half)) { ok = cuda_fail(r, errbuf, "order streams"); break; }
+        if (k >= 2 && zsk_cuda_stream_wait_event(r->cx, ZSK_STREAM_COMPUTE, EV_D2H0 + half)) { ok = cuda_fail(r, errbuf, "order streams"); break; }
+        uint8_t *stage = r->g_out + (size_t)half * chunk;
+        zsk_decode_args da;
+        memset(&da, 0, sizeof(da));
+        da.c_off = r->g_coff;
+        da.d_off = r->g_doff;
+        da.comp = img;
+        da.comp_base = r->c_off[img_lo];
+        da.dst = stage;
+        da.dst_base = r->d_off[a];
+        da.first_frame = (uint32_t)a;
+        da.njobs = (uint32_t)(b - a);
+        da.status = r->g_job_status + (a - lo);
+        const size_t nbytes = (size_t)(r->d_off[b] - r->d_off[a]);
+        if (zsk_cuda_launch_decode(r->cx, r->codec, &da, ZSK_STREAM_COMPUTE) ||
+            zsk_cuda_event_record(r->cx, EV_DEC0 + half, ZSK_STREAM_COMPUTE) ||
+            zsk_cuda_stream_wait_event(r->cx, ZSK_STREAM_D2H, EV_DEC0 + half) ||
+            zsk_cuda_memcpy_async(r->cx, dst + (r->d_off[a] - r->d_off[lo]), stage, nbytes, ZSK_D2H, ZSK_STREAM_D2H) ||
+            zsk_cuda_event_record(r->cx, EV_D2H0 + half, ZSK_STREAM_D2H)) {
+            ok = cuda_fail(r, errbuf, "decompress frame");
+            break;
+        }
+        a = b;
+        b = next_b;
+        k++;
+    }
+#undef CHUNK_END
+    if (ok)
+        ok = finish_decode(r, (uint32_t)nfr, errbuf);
+    if (zsk_cuda_stream_sync(r->cx, ZSK_STREAM_D2H) && ok)
+        ok = cuda_fail(r, errbuf, "copy to host");
+    if (!r->mem_image) {
+        zsk_cuda_stream_sync(r->cx, ZSK_STREAM_H2D);
+        r->stage_inflight = 0;
+    }
+    if (ok && !resident) {
+        r->res_lo = lo;
+        r->res_hi = hi;
+    }
+    return ok;
+}
+
+/* one partial frame piece -> host memory (through the decoded-frame cache) */
+static bool partial_to_host(zseek_reader_t *r, uint64_t f, size_t in_frame, size_t n, uint8_t *dst, void *call_data, char *errbuf)
+{
+    if (cache_find(r, f) < 0 && !fill_window(r, f, f + 1, false, call_data, errbuf))
+        return false;
+    if (zsk_cuda_memcpy_async(r->cx, dst, slot_ptr(r, r->frame_slot[f]) + in_frame, n, ZSK_D2H, ZSK_STREAM_COMPUTE) ||
+        zsk_cuda_stream_sync(r->cx, ZSK_STREAM_COMPUTE))
+        return cuda_fail(r, errbuf, "copy frame");
+    return true;
+}
+
+/* [offset, offset+count) -> host memory; count already clipped to EOF and > 0 */
+static bool read_range_host(zseek_reader_t *r, uint8_t *dst, size_t count, size_t offset, void *call_data, char *errbuf)
+{
+    uint64_t f0 = (uint64_t)st_lookup(r, offset), f1 = (uint64_t)st_lookup(r, offset + count - 1);
+    if (!in_shard(r, f0, errbuf) || !in_shard(r, f1, errbuf))
+        return false;
+    size_t end = offset + count;
+    uint64_t full_lo = f0, full_hi = f1 + 1;
+    if (offset != r->d_off[f0]) {
+        size_t n = MIN(end, (size_t)r->d_off[f0 + 1]) - offset;
+        if (!partial_to_host(r, f0, offset - (size_t)r->d_off[f0], n, dst, call_data, errbuf))
+            return false;
+        full_lo = f0 + 1;
+    }
+    if (full_hi > full_lo && end != r->d_off[f1 + 1]) {
+        size_t start = (size_t)r->d_off[f1];
+        if (!partial_to_host(r, f1, 0, end - start, dst + (start - offset), call_data, errbuf))
+            return false;
+        full_hi = f1;
+    }
+    /* a window of compressed bytes larger than this is streamed piecewise instead of being made resident at once */
+    const size_t budget = (size_t)16 << 30;
+    while (full_lo < full_hi) {
+        uint64_t hi = full_hi;
+        if (!(full_lo >= r->res_lo && hi <= r->res_hi) && r->c_off[hi] - r->c_off[full_lo] > budget) {
+            hi = full_lo + 1;
+            while (hi < full_hi && r->c_off[hi + 1] - r->c_off[full_lo] <= budget)
+                hi++;
+        }
+        if (!stream_frames_to_host(r, full_lo, hi, dst + (r->d_off[full_lo] - offset), call_data, errbuf))
+            return false;
+        full_lo = hi;
+    }
+    return true;
+}
+
 ssize_t zseek_b200_read_range(zseek_reader_t *r, void *buf, size_t count, size_t offset, void *call_data,
                               char errbuf[ZSEEK_ERRBUF_SIZE])
 {
@@ -936,42 +1092,8 @@ ssize_t zseek_b200_read_range(zseek_reader_t *r, void *buf, size_t count, size_t
             ret = (ssize_t)count;
         goto out;
     }
-    /* host destination: decode chunk k into one half of a device staging buffer on the compute
-     * stream while the D2H stream drains chunk k-1 from the other half */
-    {
-        size_t chunk = (size_t)64 << 20;
-        if (chunk < (size_t)r->max_dsize * 2)
-            chunk = (size_t)r->max_dsize * 2;
-        if (!ensure_out(r, 2 * chunk, errbuf))
-            goto out;
-        size_t done = 0;
-        unsigned k = 0;
-        bool ok = true;
-        while (done < count && ok) {
-            /* chunk boundaries fall on frame boundaries so that each piece is whole frames + edges */
-            size_t want = MIN(chunk, count - done);
-            if (done + want < count) {
-                uint64_t fl = (uint64_t)st_lookup(r, offset + done + want);
-                size_t cut = (size_t)r->d_off[fl];
-                if (cut > offset + done)
-                    want = cut - (offset + done);
-            }
-            const int half = (int)(k & 1);
-            uint8_t *stage = r->g_out + (size_t)half * chunk;
-            /* this half was last drained by the D2H copy of chunk k-2 */
-            if (k >= 2 && zsk_cuda_event_sync(r->cx, half)) { ok = cuda_fail(r, errbuf, "copy to host"); break; }
-            ok = read_range_device(r, stage, want, offset + done, call_data, errbuf); /* returns with the chunk decoded */
-            if (!ok) break;
-            if (zsk_cuda_memcpy_async(r->cx, (uint8_t *)buf + done, stage, want, ZSK_D2H, ZSK_STREAM_D2H) ||
-                zsk_cuda_event_record(r->cx, half, ZSK_STREAM_D2H)) { ok = cuda_fail(r, errbuf, "copy to host"); break; }
-            done += want;
-            k++;
-        }
-        if (zsk_cuda_stream_sync(r->cx, ZSK_STREAM_D2H) && ok)
-            ok = cuda_fail(r, errbuf, "copy to host");
-        if (ok)
-            ret = (ssize_t)count;
-    }
+    if (read_range_host(r, buf, count, offset, call_data, errbuf))
+        ret = (ssize_t)count;
 out:
     pthread_mutex_unlock(&r->lock);
     return ret;

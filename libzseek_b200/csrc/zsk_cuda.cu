@@ -106,6 +106,10 @@ int zsk_cuda_ctx_create(int device, zsk_cuda_ctx **out, char *err, size_t errlen
     }
     CK0(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, zsk_lz4_decode_lockstep_kernel, ZSK_LZ4_CTA_THREADS, 0));
     if (per_sm < 1) per_sm = 1;
+    if (const char *g = getenv("ZSEEK_B200_LZ4_CTAS_PER_SM")) { /* tuning knob: resident LZ4 CTAs per SM */
+        int v = atoi(g);
+        if (v >= 1 && v < per_sm) per_sm = v;
+    }
     cx->lz4_ctas = per_sm * cx->sm_count;
     CK0(cudaMalloc((void **)&cx->scratch, (size_t)cx->zstd_ctas * ZSK_LIT_SCRATCH + ZSK_PAD_BACK));
 #undef CK0
@@ -208,6 +212,13 @@ int zsk_cuda_event_record(zsk_cuda_ctx *cx, int ev, int stream)
 {
     CK(cx, cudaSetDevice(cx->device));
     CK(cx, cudaEventRecord(cx->user_ev[ev], cx->streams[stream]));
+    return 0;
+}
+
+int zsk_cuda_stream_wait_event(zsk_cuda_ctx *cx, int stream, int ev)
+{
+    CK(cx, cudaSetDevice(cx->device));
+    CK(cx, cudaStreamWaitEvent(cx->streams[stream], cx->user_ev[ev], 0));
     return 0;
 }
 

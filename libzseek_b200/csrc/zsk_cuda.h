@@ -37,9 +37,10 @@ int zsk_cuda_memcpy_async(zsk_cuda_ctx *cx, void *dst, const void *src, size_t n
 int zsk_cuda_stream_sync(zsk_cuda_ctx *cx, int stream);
 int zsk_cuda_stream_wait(zsk_cuda_ctx *cx, int waiter, int signaler); /* waiter waits for work queued on signaler so far */
 /* a small pool of user events: record on a stream, block the host until it has completed */
-#define ZSK_NEVENTS 4
+#define ZSK_NEVENTS 8
 int zsk_cuda_event_record(zsk_cuda_ctx *cx, int ev, int stream);
 int zsk_cuda_event_sync(zsk_cuda_ctx *cx, int ev);
+int zsk_cuda_stream_wait_event(zsk_cuda_ctx *cx, int stream, int ev); /* stream waits for the event's latest record */
 /* 1 = device memory, 0 = host (pageable or pinned), <0 = error */
 int zsk_cuda_pointer_is_device(zsk_cuda_ctx *cx, const void *p);
 
