@@ -239,3 +239,24 @@ def test_round_trip_256mib(lib, codec, level, frame, torch_cuda):
             k, a = int(res[i]), int(offs[i]) % len(tile)
             assert k == min(4096, frame - int(offs[i]) % frame)
             assert (o[i, :k] == src[a:a + k]).all() if a + k <= len(tile) else True
+
+
+# --------------------------------------------------------------------------- the reference's own integration test
+@pytest.mark.parametrize("flag", ["--lz4", "--zstd"])
+def test_reference_example_binary_runs_against_b200_reader(flag, tmp_path, torch_cuda):
+    """BASELINE configs[0]: the UNMODIFIED reference test/example.c (compiled by oracle/Makefile where
+    /root/reference exists) with its six reader symbols bound to libzseek_b200.so and its writer symbols to
+    the reference build: compress with the reference writer, scan with 4 KiB zseek_preads (cache_size 1)
+    through the CUDA path, memcmp every chunk, print SUCCESS (reference test/example.c:19-122,248-263)."""
+    import subprocess
+    from conftest import ROOT
+    exe = os.path.join(ROOT, "oracle", "_ref", "example_b200")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/example_b200 not built (needs /root/reference at build time)")
+    from datagen import zsyn
+    src = tmp_path / "input.bin"
+    src.write_bytes(zsyn.gen(64 << 20) if flag == "--lz4" else zsyn.gen(24 << 20))   # 64 MiB synthetic compressible file
+    needed = subprocess.run(["ldd", exe], capture_output=True, text=True).stdout
+    assert "libzseek_b200.so" in needed
+    p = subprocess.run([exe, flag, str(src)], capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0 and "SUCCESS" in p.stdout, (p.stdout, p.stderr)
