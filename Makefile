@@ -2,7 +2,8 @@
 NVCC     ?= nvcc
 CC       ?= gcc
 ARCH     := -gencode arch=compute_100a,code=sm_100a
-NVFLAGS  := $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC,-fvisibility=hidden,-Wall
+EXTRA    ?=
+NVFLAGS  := $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC,-fvisibility=hidden,-Wall $(EXTRA)
 CFLAGS   := -std=c11 -O2 -g -fPIC -fvisibility=hidden -Wall -Wextra -Iinclude
 SRC      := libzseek_b200/csrc
 OUT      := libzseek_b200/libzseek_b200.so
@@ -21,7 +22,13 @@ $(OUT): $(SRC)/zsk_cuda.o $(SRC)/reader.o
 oracle:
 	$(MAKE) -C oracle
 
+# experiment build: make alt EXTRA="-DZSK_LZ4_MIN_CTAS=16"  ->  libzseek_b200/libzseek_b200_alt.so (select with ZSEEK_B200_LIB)
+alt:
+	$(NVCC) $(NVFLAGS) -c $(SRC)/zsk_cuda.cu -o $(SRC)/zsk_cuda_alt.o
+	$(CC) $(CFLAGS) -c $(SRC)/reader.c -o $(SRC)/reader_alt.o
+	$(NVCC) $(ARCH) -shared -o libzseek_b200/libzseek_b200_alt.so $(SRC)/zsk_cuda_alt.o $(SRC)/reader_alt.o -lpthread
+
 clean:
 	rm -f $(SRC)/*.o $(OUT)
 
-.PHONY: all oracle clean
+.PHONY: all alt oracle clean

@@ -103,8 +103,9 @@ int zsk_cuda_ctx_create(int device, zsk_cuda_ctx **out, char *err, size_t errlen
     if (const char *g = getenv("ZSEEK_B200_LZ4_GROUP")) {
         int v = atoi(g);
         if (v == 4 || v == 8 || v == 16 || v == 32) cx->lz4_group = v;   /* plain per-group variants, for A/B runs */
+        if (v == 104 || v == 116) cx->lz4_group = v;                     /* lock-step variants with 4 / 16 lanes per frame */
     }
-    CK0(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, zsk_lz4_decode_lockstep_kernel, ZSK_LZ4_CTA_THREADS, 0));
+    CK0(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, zsk_lz4_decode_lockstep_kernel<8>, ZSK_LZ4_CTA_THREADS, 0));
     if (per_sm < 1) per_sm = 1;
     if (const char *g = getenv("ZSEEK_B200_LZ4_CTAS_PER_SM")) { /* tuning knob: resident LZ4 CTAs per SM */
         int v = atoi(g);
@@ -259,7 +260,7 @@ int zsk_cuda_launch_decode(zsk_cuda_ctx *cx, int codec, const zsk_decode_args *a
     cudaStream_t s = cx->streams[stream];
     CK(cx, cudaEventRecord(cx->k0, s));
     if (codec == ZSK_CODEC_LZ4) {
-        const unsigned frames_per_cta = ZSK_LZ4_CTA_THREADS / (unsigned)(cx->lz4_group ? cx->lz4_group : 8);
+        const unsigned frames_per_cta = ZSK_LZ4_CTA_THREADS / (unsigned)(cx->lz4_group ? cx->lz4_group % 100 : 8);
         unsigned ctas = (a.njobs + frames_per_cta - 1) / frames_per_cta;
         if (ctas > (unsigned)cx->lz4_ctas) ctas = (unsigned)cx->lz4_ctas;
         switch (cx->lz4_group) {
@@ -267,7 +268,9 @@ int zsk_cuda_launch_decode(zsk_cuda_ctx *cx, int codec, const zsk_decode_args *a
         case 16: zsk_lz4_decode_kernel<16><<<ctas, ZSK_LZ4_CTA_THREADS, 0, s>>>(a); break;
         case 32: zsk_lz4_decode_kernel<32><<<ctas, ZSK_LZ4_CTA_THREADS, 0, s>>>(a); break;
         case 8: zsk_lz4_decode_kernel<8><<<ctas, ZSK_LZ4_CTA_THREADS, 0, s>>>(a); break;
-        default: zsk_lz4_decode_lockstep_kernel<<<ctas, ZSK_LZ4_CTA_THREADS, 0, s>>>(a); break;
+        case 104: zsk_lz4_decode_lockstep_kernel<4><<<ctas, ZSK_LZ4_CTA_THREADS, 0, s>>>(a); break;
+        case 116: zsk_lz4_decode_lockstep_kernel<16><<<ctas, ZSK_LZ4_CTA_THREADS, 0, s>>>(a); break;
+        default: zsk_lz4_decode_lockstep_kernel<8><<<ctas, ZSK_LZ4_CTA_THREADS, 0, s>>>(a); break;
         }
     } else if (codec == ZSK_CODEC_ZSTD) {
         unsigned ctas = a.njobs < (unsigned)cx->zstd_ctas ? a.njobs : (unsigned)cx->zstd_ctas;

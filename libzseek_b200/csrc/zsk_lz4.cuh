@@ -221,12 +221,15 @@ __global__ void __launch_bounds__(ZSK_LZ4_CTA_THREADS) zsk_lz4_decode_kernel(zsk
  */
 enum { ZSK_LZ4_S_FETCH = 0, ZSK_LZ4_S_BLOCK = 1, ZSK_LZ4_S_SEQ = 2, ZSK_LZ4_S_DONE = 3 };
 
-__global__ void __launch_bounds__(ZSK_LZ4_CTA_THREADS) zsk_lz4_decode_lockstep_kernel(zsk_decode_args a)
+#ifndef ZSK_LZ4_MIN_CTAS
+#define ZSK_LZ4_MIN_CTAS 12
+#endif
+template <unsigned G>
+__global__ void __launch_bounds__(ZSK_LZ4_CTA_THREADS, ZSK_LZ4_MIN_CTAS) zsk_lz4_decode_lockstep_kernel(zsk_decode_args a)
 {
-    constexpr unsigned G = 8;
     const unsigned lane = threadIdx.x & 31;
     const unsigned gl = lane & (G - 1);
-    const unsigned gmask = 0xFFu << (lane & ~(G - 1));
+    const unsigned gmask = ((1u << G) - 1u) << (lane & ~(G - 1));
     /* per-group state, identical in the 8 lanes of a group */
     int state = ZSK_LZ4_S_FETCH;
     const uint8_t *src = nullptr; /* frame start */
@@ -234,7 +237,8 @@ __global__ void __launch_bounds__(ZSK_LZ4_CTA_THREADS) zsk_lz4_decode_lockstep_k
     uint32_t n = 0, ip = 0, bend = 0, op = 0, cap = 0, job = 0, flags = 0, max_block = 0;
     uint64_t content_size = 0;
     for (;;) {
-        if (__all_sync(ZSK_FULL, state == ZSK_LZ4_S_DONE)) break; /* also the per-trip convergence point */
+        __syncwarp(); /* per-trip convergence point; orders the previous trip's stores before this trip's loads */
+        if (__all_sync(ZSK_FULL, state == ZSK_LZ4_S_DONE)) break;
         int st = ZSK_ST_OK;
         bool frame_end = false;
         if (state == ZSK_LZ4_S_SEQ) {
@@ -248,24 +252,22 @@ __global__ void __launch_bounds__(ZSK_LZ4_CTA_THREADS) zsk_lz4_decode_lockstep_k
                 fast = off >= ll + ml && off <= op + ll;
             }
             if (fast) {
-                const uint8_t *lp = src + ip + 1;
-                uint8_t *o = out + op;
-                const bool l0 = gl < ll, l1 = gl + 8 < ll;
-                uint32_t a0 = 0, a1 = 0;
-                if (l0) a0 = ZSK_LDG(lp + gl);
-                if (l1) a1 = ZSK_LDG(lp + gl + 8);
-                const uint8_t *m = o + ll - off; /* disjoint from [o, o + ll + ml) */
-                const bool m0 = gl < ml, m1 = gl + 8 < ml, m2 = gl + 16 < ml;
-                uint32_t b0 = 0, b1 = 0, b2 = 0;
-                if (m0) b0 = m[gl];
-                if (m1) b1 = m[gl + 8];
-                if (m2) b2 = m[gl + 16];
-                if (l0) o[gl] = (uint8_t)a0;
-                if (l1) o[gl + 8] = (uint8_t)a1;
+                /* predicated, branch-free: ceil(14/G) literal passes and ceil(18/G) match passes; every load is
+                 * issued before the first store */
+                constexpr unsigned LP = (14 + G - 1) / G, MP = (18 + G - 1) / G;
+                const uint8_t *lp = src + ip + 1 + gl;
+                uint8_t *o = out + op + gl;
+                const uint8_t *m = o + ll - off; /* match source, disjoint from [o, o + ll + ml) */
+                uint32_t lv[LP], mv[MP];
+#pragma unroll
+                for (unsigned k = 0; k < LP; k++) lv[k] = (gl + k * G < ll) ? ZSK_LDG(lp + k * G) : 0;
+#pragma unroll
+                for (unsigned k = 0; k < MP; k++) mv[k] = (gl + k * G < ml) ? m[k * G] : 0;
+#pragma unroll
+                for (unsigned k = 0; k < LP; k++) if (gl + k * G < ll) o[k * G] = (uint8_t)lv[k];
                 o += ll;
-                if (m0) o[gl] = (uint8_t)b0;
-                if (m1) o[gl + 8] = (uint8_t)b1;
-                if (m2) o[gl + 16] = (uint8_t)b2;
+#pragma unroll
+                for (unsigned k = 0; k < MP; k++) if (gl + k * G < ml) o[k * G] = (uint8_t)mv[k];
                 ip = after + 2;
                 op += ll + ml;
             } else {
@@ -311,8 +313,9 @@ __global__ void __launch_bounds__(ZSK_LZ4_CTA_THREADS) zsk_lz4_decode_lockstep_k
                         }
                     }
                 }
+                __syncwarp(gmask);
             }
-            __syncwarp(gmask); /* this step's bytes are visible to the group's later match loads */
+            /* fast-path stores need no group barrier of their own: every trip begins with a full-warp barrier */
         } else if (state == ZSK_LZ4_S_BLOCK) {
             if (bend && (flags & 16)) { /* block checksum after the compressed block just finished */
                 if (n - ip < 4) st = ZSK_ST_TRUNC; else ip += 4;

@@ -11,12 +11,13 @@
  *   parallel fill of the 2^maxBits table        (Predefined / RLE / FSE_Compressed / Repeat)
  *   lanes 0..3 decode the 4 Huffman streams
  *   ------------------------------ __syncthreads ------------------------------
- *   executes sequence chunk c-1:                lane 0 decodes sequence chunk c from the backward
- *   literal copy + match copy, 32 lanes         bitstream (3 interleaved FSE states), resolves
- *   cooperating, warp-level sync only           repeat-offsets, writes {LL, ML, offset} to smem
+ *   executes sequence chunk c-1, FOUR           lane 0 decodes sequence chunk c from the backward
+ *   sequences per trip (8 lanes each) when      bitstream (3 interleaved FSE states, one 8-byte
+ *   they are independent, else one by one       table load per state), resolves repeat-offsets,
+ *   with 32 lanes; warp-level sync only         writes {LL, ML, offset} to smem
  *   ------------------------------ __syncthreads (per chunk) ------------------
  *
- * All tables live in shared memory (Huffman 4 KiB, FSE 5 KiB, two sequence chunks 6 KiB); Huffman
+ * All tables live in shared memory (Huffman 4 KiB, FSE 10 KiB, two sequence chunks 3 KiB); Huffman
  * output goes to a per-CTA literal scratch in HBM (L2-resident, <= 128 KiB), the frame's output is
  * written straight to its final place and re-read from L1/L2 for match copies (offsets reach up to
  * the whole frame, far beyond what shared memory could hold for 256 KiB - 1 MiB frames).
@@ -28,16 +29,16 @@
 
 #define ZSK_ZSTD_MAGIC 0xFD2FB528u
 #define ZSK_ZSTD_CTA_THREADS 64
-#define ZSK_SEQ_CHUNK 256
+#define ZSK_SEQ_CHUNK 128
 #define ZSK_BLOCK_MAX (128u << 10)
 
 struct zsk_zstd_smem {
     uint16_t huf[2048];                   /* sym | nbBits << 8 */
-    uint32_t fse_ll[512];                 /* sym | nbBits << 8 | base << 16 */
-    uint32_t fse_ml[512];
-    uint32_t fse_of[256];
-    uint32_t wtab[64];                    /* FSE table of the Huffman weights */
-    uint32_t seq[2][ZSK_SEQ_CHUNK][3];    /* literal length, match length, offset */
+    uint2 fse_ll[512];                    /* x = base value of the code, y = next-state base | nbBits << 16 | extra bits << 24 */
+    uint2 fse_ml[512];
+    uint2 fse_of[256];
+    uint32_t wtab[64];                    /* FSE table of the Huffman weights: sym | nbBits << 8 | base << 16 */
+    uint32_t seq[2][ZSK_SEQ_CHUNK][3];    /* literal length, match length, offset; doubles as table-build scratch in stage 1 */
     uint16_t huf_start[256];
     uint8_t weights[256];
     int16_t probs[64];                    /* sequence-table build scratch (warp 1) */
@@ -94,6 +95,18 @@ static __device__ __forceinline__ uint32_t zsk_bits_read(zsk_bits &b, uint32_t n
     b.pos -= (int32_t)n;
     uint64_t v = b.win >> (unsigned)(b.pos - b.wbase);
     return (uint32_t)v & (uint32_t)((1ull << n) - 1);
+}
+
+/* unchecked read; the caller has called zsk_bits_ensure for the sum of the following reads */
+static __device__ __forceinline__ uint32_t zsk_bits_take(zsk_bits &b, uint32_t n) /* n <= 31 */
+{
+    b.pos -= (int32_t)n;
+    return (uint32_t)(b.win >> (unsigned)(b.pos - b.wbase)) & ((1u << n) - 1u);
+}
+
+static __device__ __forceinline__ void zsk_bits_ensure(zsk_bits &b, int32_t need) /* need <= 57 */
+{
+    if (b.pos - b.wbase < need) zsk_bits_refill(b);
 }
 
 static __device__ __forceinline__ int zsk_bitlen(uint32_t v) { return 32 - __clz((int)v); }
@@ -170,6 +183,22 @@ static __device__ const uint32_t ZSK_LL_BASE[36] = { 0,1,2,3,4,5,6,7,8,9,10,11,1
 static __device__ const uint8_t ZSK_LL_BITS[36] = { 0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,1,1,1,1,2,2,3,3,4,6,7,8,9,10,11,12,13,14,15,16 };
 static __device__ const uint32_t ZSK_ML_BASE[53] = { 3,4,5,6,7,8,9,10,11,12,13,14,15,16,17,18,19,20,21,22,23,24,25,26,27,28,29,30,31,32,33,34,35,37,39,41,43,47,51,59,67,83,99,131,259,515,1027,2051,4099,8195,16387,32771,65539 };
 static __device__ const uint8_t ZSK_ML_BITS[53] = { 0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,1,1,1,1,2,2,3,3,4,4,5,7,8,9,10,11,12,13,14,15,16 };
+
+/* Expands a built table (sym | nb << 8 | base << 16) into decode entries that carry the code's base value and
+ * extra-bit count, so the sequence decoder needs one 8-byte shared-memory load per state.  kind: 0 LL, 1 OF, 2 ML.
+ * Executed by all 32 lanes of the building warp. */
+static __device__ __forceinline__ void zsk_fse_expand(uint2 *dst, const uint32_t *tmp, int log, int kind, unsigned lane)
+{
+    const uint32_t size = 1u << log;
+    for (uint32_t i = lane; i < size; i += 32) {
+        const uint32_t e = tmp[i], sym = e & 0xff, nb = (e >> 8) & 0xff, base = e >> 16;
+        uint32_t bv, xb;
+        if (kind == 0) { bv = ZSK_LL_BASE[sym]; xb = ZSK_LL_BITS[sym]; }
+        else if (kind == 2) { bv = ZSK_ML_BASE[sym]; xb = ZSK_ML_BITS[sym]; }
+        else { bv = 1u << sym; xb = sym; }
+        dst[i] = make_uint2(bv, base | (nb << 16) | (xb << 24));
+    }
+}
 
 /* One of the three sequence tables.  Single thread.  Advances *ip past the description. */
 static __device__ int zsk_seq_table(uint32_t *tab, int32_t *log_io, int mode, const uint8_t *p, uint32_t n, uint32_t *ip,
@@ -417,11 +446,25 @@ static __device__ int zsk_zstd_block(zsk_zstd_smem &S, const uint8_t *__restrict
                 }
             }
         }
-    } else if (lane == 0 && nseq) {
-        st = zsk_seq_table(S.fse_ll, &S.log_ll, (modes >> 6) & 3, p, n, &sp, ZSK_LL_DEF, 36, 6, 9, 35, S.probs, S.next);
-        if (!st) st = zsk_seq_table(S.fse_of, &S.log_of, (modes >> 4) & 3, p, n, &sp, ZSK_OF_DEF, 29, 5, 8, 31, S.probs, S.next);
-        if (!st) st = zsk_seq_table(S.fse_ml, &S.log_ml, (modes >> 2) & 3, p, n, &sp, ZSK_ML_DEF, 53, 6, 9, 52, S.probs, S.next);
-        S.bs_start = sp;
+    } else if (nseq) {
+        /* warp 1: lane 0 parses + builds each table into scratch, then all 32 lanes expand it */
+        uint32_t *tmp = &S.seq[0][0][0];
+#pragma unroll
+        for (int t = 0; t < 3; t++) {
+            const int mode = (modes >> (6 - 2 * t)) & 3;
+            int32_t *logp = t == 0 ? &S.log_ll : t == 1 ? &S.log_of : &S.log_ml;
+            uint2 *dst = t == 0 ? S.fse_ll : t == 1 ? S.fse_of : S.fse_ml;
+            if (lane == 0 && !st) {
+                if (t == 0) st = zsk_seq_table(tmp, logp, mode, p, n, &sp, ZSK_LL_DEF, 36, 6, 9, 35, S.probs, S.next);
+                else if (t == 1) st = zsk_seq_table(tmp, logp, mode, p, n, &sp, ZSK_OF_DEF, 29, 5, 8, 31, S.probs, S.next);
+                else st = zsk_seq_table(tmp, logp, mode, p, n, &sp, ZSK_ML_DEF, 53, 6, 9, 52, S.probs, S.next);
+            }
+            __syncwarp();
+            st = __shfl_sync(ZSK_FULL, st, 0);
+            if (!st && mode != 3) zsk_fse_expand(dst, tmp, *logp, t, lane);
+            __syncwarp();
+        }
+        if (lane == 0) S.bs_start = sp;
     }
     if ((st = zsk_cta_status(S, st))) return st;
 
@@ -448,16 +491,16 @@ static __device__ int zsk_zstd_block(zsk_zstd_smem &S, const uint8_t *__restrict
                     const uint32_t cnt = min(nseq - first, (uint32_t)ZSK_SEQ_CHUNK);
                     uint32_t r0 = S.rep[0], r1 = S.rep[1], r2 = S.rep[2];
                     for (uint32_t i = 0; i < cnt; i++) {
-                        const uint32_t el = S.fse_ll[sl], eo = S.fse_of[so], em = S.fse_ml[sm];
-                        const uint32_t lc = el & 0xff, oc = eo & 0xff, mc = em & 0xff;
-                        if (lc > 35 || oc > 31 || mc > 52) { st = ZSK_ST_TABLE; break; }
-                        const uint32_t ov = (1u << oc) + zsk_bits_read(b, oc);
-                        const uint32_t mlen = ZSK_ML_BASE[mc] + zsk_bits_read(b, ZSK_ML_BITS[mc]);
-                        const uint32_t llen = ZSK_LL_BASE[lc] + zsk_bits_read(b, ZSK_LL_BITS[lc]);
+                        const uint2 el = S.fse_ll[sl], eo = S.fse_of[so], em = S.fse_ml[sm];
+                        zsk_bits_ensure(b, 47);                               /* offset extra <= 31, match extra <= 16 */
+                        const uint32_t ov = eo.x + zsk_bits_take(b, eo.y >> 24);
+                        const uint32_t mlen = em.x + zsk_bits_take(b, em.y >> 24);
+                        zsk_bits_ensure(b, 42);                               /* literal extra <= 16, state bits <= 9 + 9 + 8 */
+                        const uint32_t llen = el.x + zsk_bits_take(b, el.y >> 24);
                         if (first + i + 1 < nseq) {
-                            sl = (el >> 16) + zsk_bits_read(b, (el >> 8) & 0xff);
-                            sm = (em >> 16) + zsk_bits_read(b, (em >> 8) & 0xff);
-                            so = (eo >> 16) + zsk_bits_read(b, (eo >> 8) & 0xff);
+                            sl = (el.y & 0xffff) + zsk_bits_take(b, (el.y >> 16) & 0xff);
+                            sm = (em.y & 0xffff) + zsk_bits_take(b, (em.y >> 16) & 0xff);
+                            so = (eo.y & 0xffff) + zsk_bits_take(b, (eo.y >> 16) & 0xff);
                         }
                         if (b.pos < 0) { st = ZSK_ST_BITSTREAM; break; }
                         uint32_t offset;
@@ -479,20 +522,65 @@ static __device__ int zsk_zstd_block(zsk_zstd_smem &S, const uint8_t *__restrict
                     if (!st && c + 1 == nchunks && b.pos != 0) st = ZSK_ST_BITSTREAM;
                 }
             } else if (c > 0) {
+                /* warp 0 executes chunk c-1 four sequences per trip: lane group g (8 lanes) takes sequence 4t+g.
+                 * Fast trip (all four): literal run <= 16, match <= 32 and every match source ends before the
+                 * first byte this trip writes -> all loads of the four sequences are in flight together, then
+                 * all stores.  Otherwise the four are executed one after another by the whole warp. */
                 const uint32_t (*q)[3] = S.seq[(c - 1) & 1];
                 const uint32_t first = (c - 1) * ZSK_SEQ_CHUNK;
                 const uint32_t cnt = min(nseq - first, (uint32_t)ZSK_SEQ_CHUNK);
-                for (uint32_t i = 0; i < cnt; i++) {
-                    const uint32_t llen = q[i][0], mlen = q[i][1], offset = q[i][2];
-                    if (llen > regen - lpos) { st = ZSK_ST_FORMAT; break; }
-                    if (llen > cap - op || mlen > cap - op - llen) { st = ZSK_ST_DST; break; }
-                    if (llen) zsk_warp_literals(out + op, L, lpos, llen, lane);
-                    op += llen; lpos += llen;
-                    if (offset > op) { st = ZSK_ST_OFFSET; break; }
-                    __syncwarp();
-                    zsk_warp_match(out, op, offset, mlen, lane);
-                    __syncwarp();
-                    op += mlen;
+                const unsigned g = lane >> 3, gl = lane & 7;
+                for (uint32_t t = 0; t < cnt && !st; t += 4) {
+                    const bool act = t + g < cnt;
+                    uint32_t llen = 0, mlen = 0, offset = 1;
+                    if (act) { llen = q[t + g][0]; mlen = q[t + g][1]; offset = q[t + g][2]; }
+                    const uint32_t len = llen + mlen;
+                    const uint32_t n0 = __shfl_sync(ZSK_FULL, len, 0), n1 = __shfl_sync(ZSK_FULL, len, 8), n2 = __shfl_sync(ZSK_FULL, len, 16),
+                                   n3 = __shfl_sync(ZSK_FULL, len, 24);
+                    const uint32_t l0 = __shfl_sync(ZSK_FULL, llen, 0), l1 = __shfl_sync(ZSK_FULL, llen, 8), l2 = __shfl_sync(ZSK_FULL, llen, 16),
+                                   l3 = __shfl_sync(ZSK_FULL, llen, 24);
+                    const uint32_t rel = (g > 0 ? n0 : 0) + (g > 1 ? n1 : 0) + (g > 2 ? n2 : 0);      /* output start inside the trip */
+                    const uint32_t lrel = (g > 0 ? l0 : 0) + (g > 1 ? l1 : 0) + (g > 2 ? l2 : 0);    /* literal start inside the trip */
+                    const uint32_t tot = n0 + n1 + n2 + n3, ltot = l0 + l1 + l2 + l3;
+                    bool ok = llen <= 16 && mlen <= 32 && offset >= rel + len && offset <= op + rel + llen;
+                    ok = ok && ltot <= regen - lpos && tot <= cap - op;
+                    if (__all_sync(ZSK_FULL, ok)) {
+                        uint8_t *o = out + op + rel + gl;
+                        const uint8_t *m = o + llen - offset;
+                        uint32_t lv[2], mv[4];
+                        if (L.ptr) {
+                            const uint8_t *lp = L.ptr + lpos + lrel + gl;
+#pragma unroll
+                            for (unsigned k = 0; k < 2; k++) lv[k] = (gl + 8 * k < llen) ? lp[8 * k] : 0;
+                        } else {
+                            lv[0] = lv[1] = L.rle;
+                        }
+#pragma unroll
+                        for (unsigned k = 0; k < 4; k++) mv[k] = (gl + 8 * k < mlen) ? m[8 * k] : 0;
+#pragma unroll
+                        for (unsigned k = 0; k < 2; k++) if (gl + 8 * k < llen) o[8 * k] = (uint8_t)lv[k];
+                        o += llen;
+#pragma unroll
+                        for (unsigned k = 0; k < 4; k++) if (gl + 8 * k < mlen) o[8 * k] = (uint8_t)mv[k];
+                        op += tot;
+                        lpos += ltot;
+                        __syncwarp();
+                    } else {
+                        const uint32_t k_end = min(4u, cnt - t);
+                        for (uint32_t k = 0; k < k_end; k++) {
+                            const uint32_t ll1 = __shfl_sync(ZSK_FULL, llen, 8 * k), ml1 = __shfl_sync(ZSK_FULL, mlen, 8 * k),
+                                           of1 = __shfl_sync(ZSK_FULL, offset, 8 * k);
+                            if (ll1 > regen - lpos) { st = ZSK_ST_FORMAT; break; }
+                            if (ll1 > cap - op || ml1 > cap - op - ll1) { st = ZSK_ST_DST; break; }
+                            if (ll1) zsk_warp_literals(out + op, L, lpos, ll1, lane);
+                            op += ll1; lpos += ll1;
+                            if (of1 > op) { st = ZSK_ST_OFFSET; break; }
+                            __syncwarp();
+                            zsk_warp_match(out, op, of1, ml1, lane);
+                            __syncwarp();
+                            op += ml1;
+                        }
+                    }
                 }
             }
             if ((st = zsk_cta_status(S, st))) return st;

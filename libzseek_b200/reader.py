@@ -11,7 +11,7 @@ import subprocess
 import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-LIB_PATH = os.path.join(ROOT, "libzseek_b200", "libzseek_b200.so")
+LIB_PATH = os.environ.get("ZSEEK_B200_LIB") or os.path.join(ROOT, "libzseek_b200", "libzseek_b200.so")
 ERRBUF = 80
 ZSTD, LZ4 = 0, 1
 
