@@ -98,6 +98,10 @@ int zsk_cuda_ctx_create(int device, zsk_cuda_ctx **out, char *err, size_t errlen
     int per_sm = 0;
     CK0(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, zsk_zstd_decode_kernel, ZSK_ZSTD_CTA_THREADS, 0));
     if (per_sm < 1) per_sm = 1;
+    if (const char *g = getenv("ZSEEK_B200_ZSTD_CTAS_PER_SM")) { /* tuning knob: resident zstd CTAs per SM */
+        int v = atoi(g);
+        if (v >= 1 && v < per_sm) per_sm = v;
+    }
     cx->zstd_ctas = per_sm * cx->sm_count;
     cx->lz4_group = 0;                   /* 0 = lock-step kernel (8 lanes per frame) */
     if (const char *g = getenv("ZSEEK_B200_LZ4_GROUP")) {

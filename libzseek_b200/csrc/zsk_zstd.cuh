@@ -492,15 +492,19 @@ static __device__ int zsk_zstd_block(zsk_zstd_smem &S, const uint8_t *__restrict
                     uint32_t r0 = S.rep[0], r1 = S.rep[1], r2 = S.rep[2];
                     for (uint32_t i = 0; i < cnt; i++) {
                         const uint2 el = S.fse_ll[sl], eo = S.fse_of[so], em = S.fse_ml[sm];
-                        zsk_bits_ensure(b, 47);                               /* offset extra <= 31, match extra <= 16 */
-                        const uint32_t ov = eo.x + zsk_bits_take(b, eo.y >> 24);
-                        const uint32_t mlen = em.x + zsk_bits_take(b, em.y >> 24);
-                        zsk_bits_ensure(b, 42);                               /* literal extra <= 16, state bits <= 9 + 9 + 8 */
-                        const uint32_t llen = el.x + zsk_bits_take(b, el.y >> 24);
+                        /* the window is refilled only when the fields about to be read do not fit what is left of it:
+                         * offset extra (<= 31) + match extra (<= 16), then literal extra (<= 16) + state bits (<= 26) */
+                        const uint32_t xo = eo.y >> 24, xm = em.y >> 24, xl = el.y >> 24;
+                        zsk_bits_ensure(b, (int32_t)(xo + xm));
+                        const uint32_t ov = eo.x + zsk_bits_take(b, xo);
+                        const uint32_t mlen = em.x + zsk_bits_take(b, xm);
+                        const uint32_t nl = (el.y >> 16) & 0xff, nm = (em.y >> 16) & 0xff, no = (eo.y >> 16) & 0xff;
+                        zsk_bits_ensure(b, (int32_t)(xl + nl + nm + no));
+                        const uint32_t llen = el.x + zsk_bits_take(b, xl);
                         if (first + i + 1 < nseq) {
-                            sl = (el.y & 0xffff) + zsk_bits_take(b, (el.y >> 16) & 0xff);
-                            sm = (em.y & 0xffff) + zsk_bits_take(b, (em.y >> 16) & 0xff);
-                            so = (eo.y & 0xffff) + zsk_bits_take(b, (eo.y >> 16) & 0xff);
+                            sl = (el.y & 0xffff) + zsk_bits_take(b, nl);
+                            sm = (em.y & 0xffff) + zsk_bits_take(b, nm);
+                            so = (eo.y & 0xffff) + zsk_bits_take(b, no);
                         }
                         if (b.pos < 0) { st = ZSK_ST_BITSTREAM; break; }
                         uint32_t offset;
