@@ -264,7 +264,7 @@ int zsk_cuda_launch_decode(zsk_cuda_ctx *cx, int codec, const zsk_decode_args *a
     cudaStream_t s = cx->streams[stream];
     CK(cx, cudaEventRecord(cx->k0, s));
     if (codec == ZSK_CODEC_LZ4) {
-        const unsigned frames_per_cta = ZSK_LZ4_CTA_THREADS / (unsigned)(cx->lz4_group ? cx->lz4_group % 100 : 8);
+        unsigned frames_per_cta = ZSK_LZ4_CTA_THREADS / (unsigned)(cx->lz4_group ? cx->lz4_group % 100 : 8);
         unsigned ctas = (a.njobs + frames_per_cta - 1) / frames_per_cta;
         if (ctas > (unsigned)cx->lz4_ctas) ctas = (unsigned)cx->lz4_ctas;
         switch (cx->lz4_group) {

@@ -391,3 +391,4 @@ __global__ void __launch_bounds__(ZSK_LZ4_CTA_THREADS, ZSK_LZ4_MIN_CTAS) zsk_lz4
         }
     }
 }
+
