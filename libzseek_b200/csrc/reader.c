@@ -105,6 +105,11 @@ struct zseek_reader {
     uint64_t ra_next;
     uint32_t ra_window, ra_max;
     size_t chunk_bytes; /* decoded bytes per pipeline stage of host-destination range reads */
+
+    /* host/device classification of caller buffers, cached per 2 MiB virtual-address block so that the hot
+     * zseek_pread path does not enter the CUDA driver (a global lock) on every call */
+    uintptr_t ptr_block[8];
+    int8_t ptr_is_dev[8];
 };
 
 /* ------------------------------------------------------------------ errors (reference src/common.c:45-54) */
@@ -375,11 +380,14 @@ static bool alloc_image(zseek_reader_t *r, uint64_t lo, uint64_t hi, char *errbu
     if (zsk_cuda_stream_sync(r->cx, ZSK_STREAM_COMPUTE)) return cuda_fail(r, errbuf, "synchronize");
     r->res_lo = r->res_hi = 0;
     if (need > r->g_comp_cap) {
+        /* grow geometrically (bounded by the whole payload): a growing read-ahead window must not reallocate every time */
+        size_t whole = (size_t)r->c_off[r->nframes] + ZSK_PAD_FRONT + ZSK_PAD_BACK;
+        size_t want = MIN(MAX(need, 2 * r->g_comp_cap), MAX(whole, need));
         zsk_cuda_free(r->cx, r->g_comp);
         r->g_comp = NULL;
         r->g_comp_cap = 0;
-        if (zsk_cuda_malloc(r->cx, (void **)&r->g_comp, need)) return cuda_fail(r, errbuf, "allocate device image");
-        r->g_comp_cap = need;
+        if (zsk_cuda_malloc(r->cx, (void **)&r->g_comp, want)) return cuda_fail(r, errbuf, "allocate device image");
+        r->g_comp_cap = want;
     }
     return true;
 }
@@ -510,6 +518,18 @@ static bool fill_window(zseek_reader_t *r, uint64_t lo, uint64_t hi, bool mirror
     return true;
 }
 
+static int buf_on_device(zseek_reader_t *r, const void *buf)
+{
+    const uintptr_t block = ((uintptr_t)buf >> 21) + 1; /* +1: 0 marks an empty cache entry */
+    const unsigned i = (unsigned)(block & 7);
+    if (r->ptr_block[i] == block)
+        return r->ptr_is_dev[i];
+    int d = zsk_cuda_pointer_is_device(r->cx, buf);
+    r->ptr_block[i] = block;
+    r->ptr_is_dev[i] = (int8_t)(d > 0);
+    return d > 0;
+}
+
 static bool in_shard(zseek_reader_t *r, uint64_t f, char *errbuf)
 {
     if (f >= r->shard_lo && f < r->shard_hi)
@@ -586,17 +606,19 @@ static zseek_reader_t *reader_open_common(zseek_reader_t *r, size_t cache_size, 
     r->shard_lo = 0;
     r->shard_hi = N;
     r->user_cache_size = cache_size;
-    /* read-ahead window: ~64 MiB of decoded frames, at most 1024 frames */
-    size_t ra = r->max_dsize ? (64u << 20) / r->max_dsize : 1;
-    ra = MAX(1, MIN(ra, 1024));
+    /* read-ahead window of a sequential scan: up to ~128 MiB of decoded frames (grows x4 per sequential miss) */
+    size_t ra = r->max_dsize ? (128u << 20) / r->max_dsize : 1;
+    ra = MAX(1, MIN(ra, 8192));
     ra = env_size("ZSEEK_B200_READAHEAD", ra);
     r->ra_max = (uint32_t)MAX(1, MIN(ra, 65536));
+    if (N && r->ra_max > N)
+        r->ra_max = (uint32_t)N;
     r->ra_window = 1;
     r->ra_next = UINT64_MAX;
-    r->nslots = (uint32_t)MAX(MAX(cache_size, r->ra_max), 1);
+    /* decoded-frame cache in HBM: what the caller asked for, and never fewer than 64 slots for device-side readers */
+    r->nslots = (uint32_t)MAX(MAX(cache_size, 64), 1);
     if (N && r->nslots > N)
         r->nslots = (uint32_t)N;
-    r->ra_max = MIN(r->ra_max, r->nslots);
     r->slot_size = ((size_t)r->max_dsize + 255) & ~(size_t)255;
     if (r->slot_size == 0)
         r->slot_size = 256;
@@ -691,6 +713,8 @@ bool zseek_reader_close(zseek_reader_t *reader, void *call_data, char errbuf[ZSE
     return true;
 }
 
+static bool stream_frames_to_host(zseek_reader_t *r, uint64_t lo, uint64_t hi, uint8_t *dst, void *call_data, char *errbuf);
+
 /* ------------------------------------------------------------------ zseek_pread (reference src/decompress.c:806-824) */
 static ssize_t pread_locked(zseek_reader_t *r, void *buf, size_t count, size_t offset, void *call_data, char *errbuf)
 {
@@ -704,7 +728,7 @@ static ssize_t pread_locked(zseek_reader_t *r, void *buf, size_t count, size_t o
         return 0; /* B3 */
     if (!in_shard(r, f, errbuf))
         return -1;
-    int on_device = zsk_cuda_pointer_is_device(r->cx, buf);
+    int on_device = buf_on_device(r, buf);
     if (!on_device && f >= r->mir_lo && f < r->mir_hi) { /* pinned window hit: plain memcpy */
         memcpy(buf, r->h_mirror + (offset - r->d_off[r->mir_lo]), n);
         return (ssize_t)n;
@@ -717,8 +741,16 @@ static ssize_t pread_locked(zseek_reader_t *r, void *buf, size_t count, size_t o
             r->ra_window = MIN(r->ra_window * 4, r->ra_max);
         else
             r->ra_window = 1;
-        uint64_t hi = MIN(f + r->ra_window, r->shard_hi);
-        if (!fill_window(r, f, hi, !on_device, call_data, errbuf))
+        uint64_t hi = MIN(f + (on_device ? MIN(r->ra_window, r->nslots) : r->ra_window), r->shard_hi);
+        if (!on_device && hi - f > 1) {
+            /* sequential host reader: decode the window through the H2D / decode / D2H pipeline straight into
+             * the pinned mirror (one contiguous copy per chunk); later reads of the window are memcpys */
+            r->mir_lo = r->mir_hi = 0;
+            if (!stream_frames_to_host(r, f, hi, r->h_mirror, call_data, errbuf))
+                return -1;
+            r->mir_lo = f;
+            r->mir_hi = hi;
+        } else if (!fill_window(r, f, hi, !on_device, call_data, errbuf))
             return -1;
         r->ra_next = hi;
         if (!on_device) {
@@ -929,9 +961,13 @@ static bool ensure_out(zseek_reader_t *r, size_t n, char *errbuf)
     zsk_cuda_free(r->cx, r->g_out);
     r->g_out = NULL;
     r->g_out_cap = 0;
-    if (zsk_cuda_malloc(r->cx, (void **)&r->g_out, n + ZSK_PAD_BACK))
-        return cuda_fail(r, errbuf, "allocate output staging");
-    r->g_out_cap = n;
+    size_t want = MAX(n, 2 * r->g_out_cap);
+    if (zsk_cuda_malloc(r->cx, (void **)&r->g_out, want + ZSK_PAD_BACK)) {
+        want = n;
+        if (zsk_cuda_malloc(r->cx, (void **)&r->g_out, want + ZSK_PAD_BACK))
+            return cuda_fail(r, errbuf, "allocate output staging");
+    }
+    r->g_out_cap = want;
     return true;
 }
 
@@ -951,6 +987,9 @@ static bool stream_frames_to_host(zseek_reader_t *r, uint64_t lo, uint64_t hi, u
     const uint64_t nfr = hi - lo;
     const bool resident = lo >= r->res_lo && hi <= r->res_hi;
     size_t chunk = MAX(r->chunk_bytes, (size_t)r->max_dsize);
+    const size_t span = (size_t)(r->d_off[hi] - r->d_off[lo]);
+    if (span < chunk) /* small windows do not need the full-size staging halves */
+        chunk = MAX(span, (size_t)r->max_dsize);
     if (!ensure_jobs(r, (uint32_t)nfr, errbuf) || !ensure_out(r, 2 * chunk, errbuf))
         return false;
     if (!resident && !alloc_image(r, lo, hi, errbuf))
@@ -1087,7 +1126,7 @@ ssize_t zseek_b200_read_range(zseek_reader_t *r, void *buf, size_t count, size_t
         goto out;
     }
     count = MIN(count, total - offset);
-    if (zsk_cuda_pointer_is_device(r->cx, buf)) {
+    if (buf_on_device(r, buf)) {
         if (read_range_device(r, buf, count, offset, call_data, errbuf))
             ret = (ssize_t)count;
         goto out;
@@ -1155,7 +1194,7 @@ ssize_t zseek_b200_pread_batch(zseek_reader_t *r, size_t n, const uint64_t *offs
     pthread_mutex_lock(&r->lock);
     ssize_t ret = -1;
     uint64_t N = r->nframes;
-    int on_device = zsk_cuda_pointer_is_device(r->cx, dst);
+    int on_device = buf_on_device(r, dst);
     uint8_t *gdst = dst;
     size_t extent = 0;
     if (!ensure_batch(r, n, errbuf))

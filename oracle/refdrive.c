@@ -88,8 +88,8 @@ EXPORT int refdrive_init(const char *so_path)
     R.read = (fn_read)dlsym(dl, "zseek_read");
     R.reader_stats = (fn_reader_stats)dlsym(dl, "zseek_reader_stats");
     R.reader_close = (fn_reader_close)dlsym(dl, "zseek_reader_close");
-    if (!R.writer_open_full || !R.write || !R.writer_close || !R.reader_open_full || !R.pread ||
-        !R.read || !R.reader_stats || !R.reader_close) {
+    /* the writer symbols are optional so that the same scan harness can be pointed at a reader-only library */
+    if (!R.reader_open_full || !R.pread || !R.read || !R.reader_stats || !R.reader_close) {
         dlclose(dl);
         return -2;
     }
@@ -127,7 +127,7 @@ EXPORT int refdrive_compress(const void *src, size_t n, int type, int level, int
                              int nb_workers, size_t min_frame_size, size_t chunk, uint8_t **out,
                              size_t *out_len, char errbuf[ZSEEK_ERRBUF_SIZE])
 {
-    if (!R.dl)
+    if (!R.dl || !R.writer_open_full || !R.write || !R.writer_close)
         return -1;
     membuf_t m = {0};
     ref_write_file_t wf = { &m, membuf_write };

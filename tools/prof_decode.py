@@ -19,7 +19,19 @@ def main():
     kind = sys.argv[1] if len(sys.argv) > 1 else "lz4"
     size = (int(sys.argv[2]) if len(sys.argv) > 2 else 256) << 20
     iters = int(sys.argv[3]) if len(sys.argv) > 3 else 3
-    tile = zsyn.gen_parallel(min(size, 64 << 20))
+    if kind.endswith("near"):
+        # diagnostic corpus: same token density as text, but every match source lies within ~600 bytes
+        rng = np.random.Generator(np.random.PCG64(5))
+        base = rng.integers(97, 123, 600, dtype=np.uint8)
+        reps = (64 << 20) // 600 + 1
+        arr = np.tile(base, reps)[:64 << 20].copy()
+        idx = np.arange(0, arr.size, 11) + rng.integers(0, 5, (arr.size + 10) // 11)
+        idx = idx[idx < arr.size]
+        arr[idx] = rng.integers(97, 123, idx.size, dtype=np.uint8)
+        tile = arr.tobytes()
+        kind = kind[:-4]
+    else:
+        tile = zsyn.gen_parallel(min(size, 64 << 20))
     codec, level, frame = {"lz4": (1, 0, 65536), "zstd3": (0, 3, 262144), "zstd19": (0, 19, 1 << 20), "lz4_1m": (1, 0, 1 << 20)}[kind]
     one = refwriter.write_parallel(tile, codec, level, frame, piece_frames=max(1, (4 << 20) // frame))
     image = refwriter.replicate(one, max(1, size // len(tile)))
