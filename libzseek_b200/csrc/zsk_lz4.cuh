@@ -241,30 +241,35 @@ __global__ void __launch_bounds__(ZSK_LZ4_CTA_THREADS, ZSK_LZ4_MIN_CTAS) zsk_lz4
         if (__all_sync(ZSK_FULL, state == ZSK_LZ4_S_DONE)) break;
         int st = ZSK_ST_OK;
         bool frame_end = false;
-        if (state == ZSK_LZ4_S_SEQ) {
-            const uint32_t tok = ZSK_LDG(src + ip);
-            uint32_t ll = tok >> 4, ml = (tok & 15) + 4;
+        /* Every trip each group reads a 16-byte window of its compressed stream with TWO coalesced loads
+         * (lane gl takes bytes ip+gl and ip+8+gl): the token, up to 13 literals and the 2-byte offset all come out
+         * of these registers by width-8 shuffles, instead of 5 separate loads that each cost one L1 wavefront
+         * per group (the kernel is L1-wavefront bound).  Groups that are not in the sequence
+         * state this trip read a harmless dummy window so that the shuffles stay warp-uniform. */
+        const bool in_seq = state == ZSK_LZ4_S_SEQ;
+        const uint8_t *wp = (in_seq ? src + ip : a.comp) + gl;
+        const uint32_t w0 = ZSK_LDG(wp), w1 = ZSK_LDG(wp + 8);
+        const uint32_t tok = __shfl_sync(ZSK_FULL, w0, 0, G);
+        const uint32_t tll = tok >> 4;
+        const uint32_t pl = (1 + tll) & 7, ph = (2 + tll) & 7;                     /* offset bytes sit at window positions 1+ll, 2+ll */
+        const uint32_t lo0 = __shfl_sync(ZSK_FULL, w0, pl, G), lo1 = __shfl_sync(ZSK_FULL, w1, pl, G);
+        const uint32_t hi0 = __shfl_sync(ZSK_FULL, w0, ph, G), hi1 = __shfl_sync(ZSK_FULL, w1, ph, G);
+        if (in_seq) {
+            uint32_t ll = tll, ml = (tok & 15) + 4;
             const uint32_t after = ip + 1 + ll;
-            bool fast = ll < 15 && ml < 19 && after + 2 < bend && ll + ml <= cap - op;
-            uint32_t off = 0;
+            uint32_t off = ((1 + ll < 8) ? lo0 : lo1) | (((2 + ll < 8) ? hi0 : hi1) << 8);
+            const bool fast = ll <= 13 && ml < 19 && after + 2 < bend && ll + ml <= cap - op && off >= ll + ml && off <= op + ll;
             if (fast) {
-                off = zsk_rd16(src + after);
-                fast = off >= ll + ml && off <= op + ll;
-            }
-            if (fast) {
-                /* predicated, branch-free: ceil(14/G) literal passes and ceil(18/G) match passes; every load is
-                 * issued before the first store */
-                constexpr unsigned LP = (14 + G - 1) / G, MP = (18 + G - 1) / G;
-                const uint8_t *lp = src + ip + 1 + gl;
+                /* predicated, branch-free: literals straight out of the window registers, ceil(18/G) match passes;
+                 * every load is issued before the first store */
+                constexpr unsigned MP = (18 + G - 1) / G;
                 uint8_t *o = out + op + gl;
                 const uint8_t *m = o + ll - off; /* match source, disjoint from [o, o + ll + ml) */
-                uint32_t lv[LP], mv[MP];
-#pragma unroll
-                for (unsigned k = 0; k < LP; k++) lv[k] = (gl + k * G < ll) ? ZSK_LDG(lp + k * G) : 0;
+                uint32_t mv[MP];
 #pragma unroll
                 for (unsigned k = 0; k < MP; k++) mv[k] = (gl + k * G < ml) ? m[k * G] : 0;
-#pragma unroll
-                for (unsigned k = 0; k < LP; k++) if (gl + k * G < ll) o[k * G] = (uint8_t)lv[k];
+                if (gl >= 1 && gl <= ll) o[-1] = (uint8_t)w0;        /* window byte gl is literal gl-1 */
+                if (gl + 7 < ll) o[7] = (uint8_t)w1;                 /* window byte 8+gl is literal 7+gl */
                 o += ll;
 #pragma unroll
                 for (unsigned k = 0; k < MP; k++) if (gl + k * G < ml) o[k * G] = (uint8_t)mv[k];
@@ -391,4 +396,5 @@ __global__ void __launch_bounds__(ZSK_LZ4_CTA_THREADS, ZSK_LZ4_MIN_CTAS) zsk_lz4
         }
     }
 }
+
 

@@ -24,6 +24,7 @@ void emu_decode(int codec, const uint8_t *comp, uint64_t comp_base, const uint64
     a.status = status; a.work_counter = &counter; a.scratch = scratch.data();
     if (codec == 1) emu::launch(dim3(ctas), dim3(ZSK_LZ4_CTA_THREADS), 0, [&] { zsk_lz4_decode_lockstep_kernel<8>(a); });
 
+
     else emu::launch(dim3(ctas), dim3(ZSK_ZSTD_CTA_THREADS), 0, [&] { zsk_zstd_decode_kernel(a); });
 }
 
