@@ -103,13 +103,15 @@ int zsk_cuda_ctx_create(int device, zsk_cuda_ctx **out, char *err, size_t errlen
         if (v >= 1 && v < per_sm) per_sm = v;
     }
     cx->zstd_ctas = per_sm * cx->sm_count;
-    cx->lz4_group = 0;                   /* 0 = lock-step kernel (8 lanes per frame) */
+    cx->lz4_group = 401;                 /* 401 = batch kernel (warp per frame, default); 1 = lock-step kernel (8 lanes per frame) */
     if (const char *g = getenv("ZSEEK_B200_LZ4_GROUP")) {
         int v = atoi(g);
         if (v == 4 || v == 8 || v == 16 || v == 32) cx->lz4_group = v;   /* plain per-group variants, for A/B runs */
         if (v == 104 || v == 116) cx->lz4_group = v;                     /* lock-step variants with 4 / 16 lanes per frame */
+        if (v == 401 || v == 1) cx->lz4_group = v;
     }
-    CK0(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, zsk_lz4_decode_lockstep_kernel<8>, ZSK_LZ4_CTA_THREADS, 0));
+    if (cx->lz4_group == 401) CK0(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, zsk_lz4_decode_batch_kernel, ZSK_LZ4_CTA_THREADS, 0));
+    else CK0(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, zsk_lz4_decode_lockstep_kernel<8>, ZSK_LZ4_CTA_THREADS, 0));
     if (per_sm < 1) per_sm = 1;
     if (const char *g = getenv("ZSEEK_B200_LZ4_CTAS_PER_SM")) { /* tuning knob: resident LZ4 CTAs per SM */
         int v = atoi(g);
@@ -264,7 +266,8 @@ int zsk_cuda_launch_decode(zsk_cuda_ctx *cx, int codec, const zsk_decode_args *a
     cudaStream_t s = cx->streams[stream];
     CK(cx, cudaEventRecord(cx->k0, s));
     if (codec == ZSK_CODEC_LZ4) {
-        unsigned frames_per_cta = ZSK_LZ4_CTA_THREADS / (unsigned)(cx->lz4_group ? cx->lz4_group % 100 : 8);
+        unsigned frames_per_cta = ZSK_LZ4_CTA_THREADS / (unsigned)(cx->lz4_group > 1 ? cx->lz4_group % 100 : 8);
+        if (cx->lz4_group == 401) frames_per_cta = ZSK_LZ4_CTA_THREADS / 32;
         unsigned ctas = (a.njobs + frames_per_cta - 1) / frames_per_cta;
         if (ctas > (unsigned)cx->lz4_ctas) ctas = (unsigned)cx->lz4_ctas;
         switch (cx->lz4_group) {
@@ -272,6 +275,7 @@ int zsk_cuda_launch_decode(zsk_cuda_ctx *cx, int codec, const zsk_decode_args *a
         case 16: zsk_lz4_decode_kernel<16><<<ctas, ZSK_LZ4_CTA_THREADS, 0, s>>>(a); break;
         case 32: zsk_lz4_decode_kernel<32><<<ctas, ZSK_LZ4_CTA_THREADS, 0, s>>>(a); break;
         case 8: zsk_lz4_decode_kernel<8><<<ctas, ZSK_LZ4_CTA_THREADS, 0, s>>>(a); break;
+        case 401: zsk_lz4_decode_batch_kernel<<<ctas, ZSK_LZ4_CTA_THREADS, 0, s>>>(a); break;
         case 104: zsk_lz4_decode_lockstep_kernel<4><<<ctas, ZSK_LZ4_CTA_THREADS, 0, s>>>(a); break;
         case 116: zsk_lz4_decode_lockstep_kernel<16><<<ctas, ZSK_LZ4_CTA_THREADS, 0, s>>>(a); break;
         default: zsk_lz4_decode_lockstep_kernel<8><<<ctas, ZSK_LZ4_CTA_THREADS, 0, s>>>(a); break;

@@ -22,7 +22,8 @@ void emu_decode(int codec, const uint8_t *comp, uint64_t comp_base, const uint64
     a.c_off = c_off; a.d_off = d_off; a.comp = comp; a.comp_base = comp_base; a.frame_ids = frame_ids;
     a.dst_offs = dst_offs; a.dst = dst; a.dst_base = dst_base; a.first_frame = first_frame; a.njobs = njobs;
     a.status = status; a.work_counter = &counter; a.scratch = scratch.data();
-    if (codec == 1) emu::launch(dim3(ctas), dim3(ZSK_LZ4_CTA_THREADS), 0, [&] { zsk_lz4_decode_lockstep_kernel<8>(a); });
+    if (codec == 1) emu::launch(dim3(ctas), dim3(ZSK_LZ4_CTA_THREADS), 0, [&] { zsk_lz4_decode_batch_kernel(a); });           /* shipped default */
+    else if (codec == 101) emu::launch(dim3(ctas), dim3(ZSK_LZ4_CTA_THREADS), 0, [&] { zsk_lz4_decode_lockstep_kernel<8>(a); }); /* alternative */
 
 
     else emu::launch(dim3(ctas), dim3(ZSK_ZSTD_CTA_THREADS), 0, [&] { zsk_zstd_decode_kernel(a); });

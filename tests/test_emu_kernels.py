@@ -29,6 +29,17 @@ def test_emulated_decode_matches_reference_output(emu, golden, name):
     assert hashlib.sha256(out.tobytes()).hexdigest() == c["input_sha256"]
 
 
+@pytest.mark.parametrize("name", ["zsyn_lz4_64k", "zsyn_lz4_256k_linked", "mix_lz4"])
+def test_emulated_lockstep_lz4_kernel(emu, golden, name):
+    """The alternative LZ4 kernel (8-lane groups in lock-step, ZSEEK_B200_LZ4_GROUP=1) stays correct too."""
+    cases, _ = golden
+    c = cases[name]
+    with OraclePort(c["image"]) as op:
+        out, status = emu_api.decode_all(emu, c["image"], 101, op.c_off, op.d_off, ctas=2)
+    assert (status == 0).all(), status
+    assert hashlib.sha256(out.tobytes()).hexdigest() == c["input_sha256"]
+
+
 def test_emulated_decode_flags_corrupt_frames(emu, golden):
     """Truncation and bit flips must end in a non-zero status, never a hang or an out-of-bounds write."""
     cases, _ = golden
