@@ -105,6 +105,7 @@ struct zseek_reader {
     uint64_t ra_next;
     uint32_t ra_window, ra_max;
     size_t chunk_bytes; /* decoded bytes per pipeline stage of host-destination range reads */
+    size_t ramp_bytes;  /* size of the first pipeline stage; stages double until they reach chunk_bytes */
 
     /* host/device classification of caller buffers, cached per 2 MiB virtual-address block so that the hot
      * zseek_pread path does not enter the CUDA driver (a global lock) on every call */
@@ -627,6 +628,7 @@ static zseek_reader_t *reader_open_common(zseek_reader_t *r, size_t cache_size, 
         r->stage_half = r->max_csize;
     r->mirror_cap = (size_t)r->ra_max * r->max_dsize;
     r->chunk_bytes = env_size("ZSEEK_B200_CHUNK_MB", 512) << 20;
+    r->ramp_bytes = env_size("ZSEEK_B200_RAMP_MB", 16) << 20;
 
     r->slot_frame = malloc(r->nslots * sizeof(int32_t));
     r->lru_prev = malloc(r->nslots * sizeof(int32_t));
@@ -1000,13 +1002,19 @@ static bool stream_frames_to_host(zseek_reader_t *r, uint64_t lo, uint64_t hi, u
     uint64_t a = lo, next_b = lo;
     unsigned k = 0;
     /* chunk k = frames [a, b): as many frames as fit `chunk` decoded bytes */
+    /* the first chunks are small and double up to `chunk`: the first D2H starts after ~1 ms instead of after the
+     * H2D + decode of a full-size chunk, which nothing overlaps */
+    size_t lim = MIN(chunk, MAX(r->ramp_bytes, (size_t)r->max_dsize));
 #define CHUNK_END(from, to)                                                                             \
     do {                                                                                                \
         (to) = (from) + 1;                                                                              \
-        while ((to) < hi && r->d_off[(to) + 1] - r->d_off[(from)] <= chunk) (to)++;                     \
+        while ((to) < hi && r->d_off[(to) + 1] - r->d_off[(from)] <= lim) (to)++;                       \
+        lim = MIN(chunk, lim * 2);                                                                      \
     } while (0)
     uint64_t b;
     CHUNK_END(a, b);
+    zsk_cuda_trace_reset(r->cx);
+    zsk_cuda_trace_mark(r->cx, ZSK_STREAM_H2D, "start", 0);
     if (!resident) {
         ok = h2d_range(r, (size_t)r->c_off[a], (size_t)(r->c_off[b] - r->c_off[a]), img + (r->c_off[a] - r->c_off[img_lo]), call_data, errbuf) &&
              (zsk_cuda_event_record(r->cx, EV_H2D0, ZSK_STREAM_H2D) == 0 || cuda_fail(r, errbuf, "order streams"));
@@ -1036,14 +1044,22 @@ static bool stream_frames_to_host(zseek_reader_t *r, uint64_t lo, uint64_t hi, u
         da.njobs = (uint32_t)(b - a);
         da.status = r->g_job_status + (a - lo);
         const size_t nbytes = (size_t)(r->d_off[b] - r->d_off[a]);
+        zsk_cuda_trace_mark(r->cx, ZSK_STREAM_H2D, "h2d queued up to chunk", k + 1);
+        zsk_cuda_trace_mark(r->cx, ZSK_STREAM_COMPUTE, "decode begin", k);
         if (zsk_cuda_launch_decode(r->cx, r->codec, &da, ZSK_STREAM_COMPUTE) ||
             zsk_cuda_event_record(r->cx, EV_DEC0 + half, ZSK_STREAM_COMPUTE) ||
-            zsk_cuda_stream_wait_event(r->cx, ZSK_STREAM_D2H, EV_DEC0 + half) ||
-            zsk_cuda_memcpy_async(r->cx, dst + (r->d_off[a] - r->d_off[lo]), stage, nbytes, ZSK_D2H, ZSK_STREAM_D2H) ||
+            zsk_cuda_stream_wait_event(r->cx, ZSK_STREAM_D2H, EV_DEC0 + half)) {
+            ok = cuda_fail(r, errbuf, "decompress frame");
+            break;
+        }
+        zsk_cuda_trace_mark(r->cx, ZSK_STREAM_COMPUTE, "decode end", k);
+        zsk_cuda_trace_mark(r->cx, ZSK_STREAM_D2H, "d2h begin", k);
+        if (zsk_cuda_memcpy_async(r->cx, dst + (r->d_off[a] - r->d_off[lo]), stage, nbytes, ZSK_D2H, ZSK_STREAM_D2H) ||
             zsk_cuda_event_record(r->cx, EV_D2H0 + half, ZSK_STREAM_D2H)) {
             ok = cuda_fail(r, errbuf, "decompress frame");
             break;
         }
+        zsk_cuda_trace_mark(r->cx, ZSK_STREAM_D2H, "d2h end", k);
         a = b;
         b = next_b;
         k++;
@@ -1053,6 +1069,7 @@ static bool stream_frames_to_host(zseek_reader_t *r, uint64_t lo, uint64_t hi, u
         ok = finish_decode(r, (uint32_t)nfr, errbuf);
     if (zsk_cuda_stream_sync(r->cx, ZSK_STREAM_D2H) && ok)
         ok = cuda_fail(r, errbuf, "copy to host");
+    zsk_cuda_trace_dump(r->cx);
     if (!r->mem_image) {
         zsk_cuda_stream_sync(r->cx, ZSK_STREAM_H2D);
         r->stage_inflight = 0;

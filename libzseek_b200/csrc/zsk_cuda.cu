@@ -11,6 +11,7 @@
 
 #include "zsk_cuda.h"
 #include "zsk_lz4.cuh"
+#include "zsk_lz4_lane.cuh"
 #include "zsk_zstd.cuh"
 #include "zsk_seek.cuh"
 
@@ -30,7 +31,13 @@ struct zsk_cuda_ctx {
     uint8_t *scratch;                    /* zstd literal scratch for zstd_ctas CTAs */
     int zstd_ctas, lz4_ctas;
     int lz4_group;                       /* lanes per LZ4 frame (ZSEEK_B200_LZ4_GROUP: 4, 8, 16 or 32) */
+    int lz4_lane_ctas;                   /* resident CTAs of the lane-per-frame kernel */
+    unsigned lz4_lane_min;               /* launches with at least this many frames use the lane-per-frame kernel */
     unsigned long long launches;
+    int trace;                           /* ZSEEK_B200_TRACE=1: timeline of the host-destination pipeline */
+    cudaEvent_t trace_ev[ZSK_NTRACE];
+    const char *trace_what[ZSK_NTRACE];
+    unsigned trace_k[ZSK_NTRACE], trace_n;
     char err[160];
 };
 
@@ -118,7 +125,23 @@ int zsk_cuda_ctx_create(int device, zsk_cuda_ctx **out, char *err, size_t errlen
         if (v >= 1 && v < per_sm) per_sm = v;
     }
     cx->lz4_ctas = per_sm * cx->sm_count;
+    /* lane-per-frame kernel: wins once there are enough frames to fill the lanes of the GPU (one frame per lane
+     * runs ~10x slower than one frame per warp, but 32x more of them run at once) */
+    CK0(cudaFuncSetAttribute(zsk_lz4_decode_lane_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ZSK_LZ4L_SMEM));
+    CK0(cudaFuncSetAttribute(zsk_lz4_decode_lane_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    CK0(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, zsk_lz4_decode_lane_kernel, ZSK_LZ4L_THREADS, ZSK_LZ4L_SMEM));
+    if (per_sm < 1) per_sm = 1;
+    if (const char *g = getenv("ZSEEK_B200_LZ4_LANE_CTAS_PER_SM")) {
+        int v = atoi(g);
+        if (v >= 1 && v < per_sm) per_sm = v;
+    }
+    cx->lz4_lane_ctas = per_sm * cx->sm_count;
+    cx->lz4_lane_min = 65536;
+    if (const char *g = getenv("ZSEEK_B200_LZ4_LANE_MIN")) cx->lz4_lane_min = (unsigned)strtoul(g, NULL, 10); /* 0 = always, huge = never */
     CK0(cudaMalloc((void **)&cx->scratch, (size_t)cx->zstd_ctas * ZSK_LIT_SCRATCH + ZSK_PAD_BACK));
+    if (const char *g = getenv("ZSEEK_B200_TRACE")) cx->trace = atoi(g);
+    if (cx->trace)
+        for (int i = 0; i < ZSK_NTRACE; i++) CK0(cudaEventCreate(&cx->trace_ev[i]));
 #undef CK0
     *out = cx;
     return 0;
@@ -141,6 +164,26 @@ void zsk_cuda_ctx_destroy(zsk_cuda_ctx *cx)
     cudaFree(cx->counters);
     cudaFree(cx->scratch);
     free(cx);
+}
+
+int zsk_cuda_trace_enabled(const zsk_cuda_ctx *cx) { return cx->trace; }
+void zsk_cuda_trace_reset(zsk_cuda_ctx *cx) { cx->trace_n = 0; }
+void zsk_cuda_trace_mark(zsk_cuda_ctx *cx, int stream, const char *what, unsigned k)
+{
+    if (!cx->trace || cx->trace_n >= ZSK_NTRACE) return;
+    cx->trace_what[cx->trace_n] = what;
+    cx->trace_k[cx->trace_n] = k;
+    cudaEventRecord(cx->trace_ev[cx->trace_n++], cx->streams[stream]);
+}
+void zsk_cuda_trace_dump(zsk_cuda_ctx *cx)
+{
+    if (!cx->trace || !cx->trace_n) return;
+    cudaDeviceSynchronize();
+    for (unsigned i = 0; i < cx->trace_n; i++) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, cx->trace_ev[0], cx->trace_ev[i]);
+        fprintf(stderr, "[zsk trace] %8.3f ms  %s %u\n", ms, cx->trace_what[i], cx->trace_k[i]);
+    }
 }
 
 const char *zsk_cuda_error(zsk_cuda_ctx *cx) { return cx ? cx->err : "no device context"; }
@@ -265,7 +308,11 @@ int zsk_cuda_launch_decode(zsk_cuda_ctx *cx, int codec, const zsk_decode_args *a
     a.scratch = cx->scratch;
     cudaStream_t s = cx->streams[stream];
     CK(cx, cudaEventRecord(cx->k0, s));
-    if (codec == ZSK_CODEC_LZ4) {
+    if (codec == ZSK_CODEC_LZ4 && cx->lz4_group == 401 && a.njobs >= cx->lz4_lane_min) {
+        unsigned ctas = (a.njobs + ZSK_LZ4L_THREADS - 1) / ZSK_LZ4L_THREADS;
+        if (ctas > (unsigned)cx->lz4_lane_ctas) ctas = (unsigned)cx->lz4_lane_ctas;
+        zsk_lz4_decode_lane_kernel<<<ctas, ZSK_LZ4L_THREADS, ZSK_LZ4L_SMEM, s>>>(a);
+    } else if (codec == ZSK_CODEC_LZ4) {
         unsigned frames_per_cta = ZSK_LZ4_CTA_THREADS / (unsigned)(cx->lz4_group > 1 ? cx->lz4_group % 100 : 8);
         if (cx->lz4_group == 401) frames_per_cta = ZSK_LZ4_CTA_THREADS / 32;
         unsigned ctas = (a.njobs + frames_per_cta - 1) / frames_per_cta;

@@ -57,6 +57,13 @@ int zsk_cuda_timer_stop(zsk_cuda_ctx *cx, int stream, float *ms); /* synchronise
  * valid after the stream was synchronised) */
 int zsk_cuda_last_decode_ms(zsk_cuda_ctx *cx, float *ms);
 
+/* diagnostic timeline (ZSEEK_B200_TRACE=1): timestamps of up to ZSK_NTRACE points queued on the streams */
+#define ZSK_NTRACE 192
+int zsk_cuda_trace_enabled(const zsk_cuda_ctx *cx);
+void zsk_cuda_trace_reset(zsk_cuda_ctx *cx);
+void zsk_cuda_trace_mark(zsk_cuda_ctx *cx, int stream, const char *what, unsigned k);
+void zsk_cuda_trace_dump(zsk_cuda_ctx *cx); /* synchronises the device; prints to stderr */
+
 #ifdef __cplusplus
 }
 #endif

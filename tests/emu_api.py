@@ -23,18 +23,21 @@ def lib():
     return L
 
 
-def decode_all(L, image: bytes, codec: int, c_off: np.ndarray, d_off: np.ndarray, ctas: int = 3):
+def decode_all(L, image: bytes, codec: int, c_off: np.ndarray, d_off: np.ndarray, ctas: int = 3, misalign: int = 0):
     """Whole-file decode with the emulated K2/K3; returns (decoded bytes, status array)."""
     n = len(c_off) - 1
     payload = int(c_off[-1])
     comp = np.zeros(FRONT_PAD + payload + BACK_PAD, dtype=np.uint8)
     comp[FRONT_PAD:FRONT_PAD + payload] = np.frombuffer(image, dtype=np.uint8, count=payload)
     total = int(d_off[-1])
-    dst = np.full(total + 64, 0xEE, dtype=np.uint8)
+    raw = np.full(total + 128, 0xEE, dtype=np.uint8)
+    lead = (-raw.ctypes.data) % 64 + misalign      # dst starts `misalign` bytes past a 64-byte boundary
+    dst = raw[lead:lead + total + 32]
     status = np.full(max(n, 1), -1, dtype=np.int32)
     c_off = np.ascontiguousarray(c_off, dtype=np.uint64)
     d_off = np.ascontiguousarray(d_off, dtype=np.uint64)
     L.emu_decode(codec, comp.ctypes.data + FRONT_PAD, 0, c_off.ctypes.data, d_off.ctypes.data, None, None,
                  dst.ctypes.data, 0, 0, n, status.ctypes.data, ctas)
     assert (dst[total:] == 0xEE).all(), "emulated kernel wrote past the end of the output"
+    assert (raw[:lead] == 0xEE).all(), "emulated kernel wrote before the start of the output"
     return dst[:total], status[:n]

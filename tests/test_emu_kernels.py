@@ -40,17 +40,43 @@ def test_emulated_lockstep_lz4_kernel(emu, golden, name):
     assert hashlib.sha256(out.tobytes()).hexdigest() == c["input_sha256"]
 
 
-def test_emulated_decode_flags_corrupt_frames(emu, golden):
+LZ4_CASES = ["tiny_lz4", "zsyn_lz4_64k", "zsyn_lz4_256k_linked", "mix_lz4"]
+
+
+@pytest.mark.parametrize("name", LZ4_CASES)
+def test_emulated_lane_lz4_kernel(emu, golden, name):
+    """The lane-per-frame LZ4 kernel (taken for launches with many frames) decodes every golden LZ4 file."""
+    cases, _ = golden
+    c = cases[name]
+    with OraclePort(c["image"]) as op:
+        out, status = emu_api.decode_all(emu, c["image"], 102, op.c_off, op.d_off, ctas=1)
+    assert (status == 0).all(), status
+    assert hashlib.sha256(out.tobytes()).hexdigest() == c["input_sha256"]
+
+
+@pytest.mark.parametrize("misalign", [1, 7, 15, 17, 31])
+def test_emulated_lane_lz4_kernel_unaligned_output(emu, golden, misalign):
+    """Frames whose output does not start on a 16-byte boundary: the head and tail go bytewise and neighbours stay intact."""
+    cases, _ = golden
+    c = cases["zsyn_lz4_4k_chunks"]
+    with OraclePort(c["image"]) as op:
+        out, status = emu_api.decode_all(emu, c["image"], 102, op.c_off, op.d_off, ctas=1, misalign=misalign)
+    assert (status == 0).all(), status
+    assert hashlib.sha256(out.tobytes()).hexdigest() == c["input_sha256"]
+
+
+@pytest.mark.parametrize("name,codec", [("zsyn_lz4_64k", None), ("zsyn_lz4_64k", 102), ("zsyn_zstd3_128k", None)])
+def test_emulated_decode_flags_corrupt_frames(emu, golden, name, codec):
     """Truncation and bit flips must end in a non-zero status, never a hang or an out-of-bounds write."""
     cases, _ = golden
-    for name in ("zsyn_lz4_64k", "zsyn_zstd3_128k"):
+    if True:
         c = cases[name]
         with OraclePort(c["image"]) as op:
             img = bytearray(c["image"])
             c0, c1 = int(op.c_off[1]), int(op.c_off[2])
             for k in range(c0 + 20, c1, 997):  # sprinkle corruption over frame 1 only
                 img[k] ^= 0x55
-            out, status = emu_api.decode_all(emu, bytes(img), op.codec, op.c_off, op.d_off, ctas=2)
+            out, status = emu_api.decode_all(emu, bytes(img), codec or op.codec, op.c_off, op.d_off, ctas=2)
             good = op.decode_all()
         assert status[0] == 0 and (status[2:] == 0).all()
         d0, d1 = int(op.d_off[1]), int(op.d_off[2])
@@ -92,3 +118,38 @@ def test_emulated_lookup_and_gather(emu, golden):
         for i in range(n):
             o, k = int(offsets[i]), int(nbytes[i])
             assert (dst[i * stride:i * stride + k] == decoded[o:o + k]).all()
+
+
+def _shapes_corpus():
+    """Every LZ4 sequence shape the lane kernel spreads over several trips: periodic runs of period 1..40 (overlapping
+    matches), long zero runs, incompressible stretches (long literal runs, raw blocks), long far matches."""
+    rng = np.random.Generator(np.random.PCG64(42))
+    parts = []
+    text = rng.integers(97, 123, 3000, dtype=np.uint8).tobytes()
+    for period in list(range(1, 41)) + [63, 64, 65, 191, 192, 193, 255, 256, 257]:
+        pat = rng.integers(0, 256, period, dtype=np.uint8).tobytes()
+        parts.append(pat * (rng.integers(2, 300) // 1) + text[:int(rng.integers(0, 40))])
+    parts.append(bytes(70000))
+    parts.append(rng.integers(0, 256, 80000, dtype=np.uint8).tobytes())
+    parts.append(text * 20)
+    for _ in range(200):   # far matches of assorted lengths separated by short literal runs
+        o = int(rng.integers(0, len(text) - 600))
+        parts.append(text[o:o + int(rng.integers(4, 600))] + rng.integers(0, 256, int(rng.integers(0, 30)), dtype=np.uint8).tobytes())
+    return b"".join(parts)
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(block_checksum=True, content_checksum=True), dict(block_size_id=5, level=9),
+                                dict(content_size=False, independent=True)])
+def test_emulated_lane_lz4_kernel_sequence_shapes(emu, kw):
+    from datagen import foreign
+    from oracle.pyapi import have_reference
+    if not have_reference():
+        pytest.skip("liblz4 frames are built through oracle/_ref's codec libraries")
+    data = _shapes_corpus()
+    image = foreign.build(data, 100000, "lz4", **kw)
+    with OraclePort(image) as op:
+        assert op.decode_all().tobytes() == data
+        for codec, mis in ((102, 0), (102, 3), (1, 0)):
+            out, status = emu_api.decode_all(emu, image, codec, op.c_off, op.d_off, ctas=1, misalign=mis)
+            assert (status == 0).all(), status
+            assert out.tobytes() == data
