@@ -106,6 +106,11 @@ struct zseek_reader {
     uint32_t ra_window, ra_max;
     size_t chunk_bytes; /* decoded bytes per pipeline stage of host-destination range reads */
     size_t ramp_bytes;  /* size of the first pipeline stage; stages double until they reach chunk_bytes */
+    /* launches of at least sort_min LZ4 frames hand the kernel a job list ordered by compressed size (largest
+     * first): the lane-per-frame kernel then runs frames of similar length side by side in a warp, warps retire
+     * as a whole and the longest frames start first.  0 = never. */
+    size_t sort_min;
+    uint64_t sorted_lo, sorted_hi; /* g_job_ids currently holds the ordered list of [sorted_lo, sorted_hi) */
 
     /* host/device classification of caller buffers, cached per 2 MiB virtual-address block so that the hot
      * zseek_pread path does not enter the CUDA driver (a global lock) on every call */
@@ -432,6 +437,7 @@ static bool ensure_jobs(zseek_reader_t *r, uint32_t n, char *errbuf)
     r->g_job_ids = NULL; r->g_job_offs = NULL; r->g_job_status = NULL;
     r->h_job_ids = NULL; r->h_job_offs = NULL; r->h_job_status = NULL;
     r->job_cap = 0;
+    r->sorted_lo = r->sorted_hi = 0;
     if (zsk_cuda_malloc(r->cx, (void **)&r->g_job_ids, cap * sizeof(uint32_t)) ||
         zsk_cuda_malloc(r->cx, (void **)&r->g_job_offs, cap * sizeof(uint64_t)) ||
         zsk_cuda_malloc(r->cx, (void **)&r->g_job_status, cap * sizeof(int32_t)) ||
@@ -462,6 +468,7 @@ static bool decode_into_cache(zseek_reader_t *r, uint32_t n, char *errbuf)
 {
     if (n == 0)
         return true;
+    r->sorted_lo = r->sorted_hi = 0; /* the job list is about to be overwritten */
     for (uint32_t i = 0; i < n; i++) {
         int32_t s = cache_take(r, r->h_job_ids[i]);
         r->h_job_offs[i] = (uint64_t)((size_t)s * r->slot_size);
@@ -629,6 +636,7 @@ static zseek_reader_t *reader_open_common(zseek_reader_t *r, size_t cache_size, 
     r->mirror_cap = (size_t)r->ra_max * r->max_dsize;
     r->chunk_bytes = env_size("ZSEEK_B200_CHUNK_MB", 512) << 20;
     r->ramp_bytes = env_size("ZSEEK_B200_RAMP_MB", 16) << 20;
+    r->sort_min = env_size("ZSEEK_B200_SORT_MIN", 65536);
 
     r->slot_frame = malloc(r->nslots * sizeof(int32_t));
     r->lru_prev = malloc(r->nslots * sizeof(int32_t));
@@ -864,6 +872,20 @@ bool zseek_b200_load(zseek_reader_t *r, size_t lo, size_t hi, void *call_data, c
 }
 
 /* whole frames [lo, hi) -> device memory, frame f at dst + d_off[f] - d_off[lo]; asynchronous part */
+/* h_job_ids[0 .. hi-lo) = frames [lo, hi) ordered by compressed size, largest first (counting sort over 512-byte
+ * size classes; stable, so equal classes stay in file order) */
+static void order_jobs_by_size(zseek_reader_t *r, uint64_t lo, uint64_t hi)
+{
+    enum { CLASSES = 4096 };
+    static _Thread_local uint32_t start[CLASSES + 1];
+    memset(start, 0, sizeof(start));
+#define SIZE_CLASS(f) ((uint32_t)MIN((uint64_t)(CLASSES - 1), (r->c_off[(f) + 1] - r->c_off[(f)]) >> 9))
+    for (uint64_t f = lo; f < hi; f++) start[CLASSES - 1 - SIZE_CLASS(f) + 1]++;
+    for (uint32_t c = 0; c < CLASSES; c++) start[c + 1] += start[c];
+    for (uint64_t f = lo; f < hi; f++) r->h_job_ids[start[CLASSES - 1 - SIZE_CLASS(f)]++] = (uint32_t)f;
+#undef SIZE_CLASS
+}
+
 static bool decode_range_device(zseek_reader_t *r, uint64_t lo, uint64_t hi, uint8_t *dst, void *call_data, char *errbuf)
 {
     if (lo >= hi)
@@ -879,6 +901,16 @@ static bool decode_range_device(zseek_reader_t *r, uint64_t lo, uint64_t hi, uin
     a.first_frame = (uint32_t)lo;
     a.njobs = (uint32_t)(hi - lo);
     a.status = r->g_job_status;
+    if (r->codec == ZSK_CODEC_LZ4 && r->sort_min && hi - lo >= r->sort_min) {
+        if (r->sorted_lo != lo || r->sorted_hi != hi) {
+            order_jobs_by_size(r, lo, hi);
+            if (zsk_cuda_memcpy_async(r->cx, r->g_job_ids, r->h_job_ids, (size_t)(hi - lo) * sizeof(uint32_t), ZSK_H2D, ZSK_STREAM_COMPUTE))
+                return cuda_fail(r, errbuf, "copy job list");
+            r->sorted_lo = lo;
+            r->sorted_hi = hi;
+        }
+        a.frame_ids = r->g_job_ids; /* job i = frame g_job_ids[i]; its bytes still land at d_off[frame] - dst_base */
+    }
     if (zsk_cuda_launch_decode(r->cx, r->codec, &a, ZSK_STREAM_COMPUTE))
         return cuda_fail(r, errbuf, "decompress frame");
     return true;
