@@ -244,6 +244,7 @@ def run_b200(args, rank, world):
         for _ in range(args.steps):
             rd.decode_frames(0, rd.frames, dev_out)                 # inputs (C+D = 6 GB) >> L2, no flush needed
             kernel_ms += rd.last_decode_ms
+        kernel_name = rd.last_decode_kernel
         dev_ms = rd.timer_stop()
         barrier()
         wall = time.perf_counter() - wall0
@@ -255,7 +256,7 @@ def run_b200(args, rank, world):
         # spot-check the bytes that were just timed against the source tile (full parity lives in tests/)
         chk = dev_out[:1 << 20].cpu().numpy()
         results[name] = dict(total=total, C=C, dev_ms=dev_ms, kernel_ms=max_over_ranks(kernel_ms), wall=wall, launches=launches,
-                             frames=rd.frames, first_mib=chk)
+                             frames=rd.frames, first_mib=chk, kernel=kernel_name)
         launches_total += launches if name == "lz4" else 0
         # ---- e2e: host buffers, H2D + decode + D2H inside the timed region (through zseek_b200_read_range)
         if name == "lz4":
@@ -362,8 +363,8 @@ def run_b200(args, rank, world):
                     "api": "zseek_b200_read_range, pinned host image -> pinned host buffer"},
             "gpu_launches": launches_total,
             "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-                         "frac": round(achieved / peak, 4), "traffic": profile_traffic("zsk_lz4_decode_kernel"),
-                         "kernel": "zsk_lz4_decode_kernel", "algorithmic_bytes_per_launch": lz["C"] + lz["total"],
+                         "frac": round(achieved / peak, 4), "traffic": profile_traffic(lz["kernel"]),
+                         "kernel": lz["kernel"], "algorithmic_bytes_per_launch": lz["C"] + lz["total"],
                          "peak_source": peak_src},
             "cpu_baseline": {"value": round(cpu["lz4"]["gbps"], 3), "unit": "GB/s", "cores": cpu["lz4"]["threads"], "kind": "reference",
                              "sample": f"first {cpu['lz4']['sample'] >> 20} MiB of the same file, one reader per thread, 1 MiB zseek_pread "
@@ -372,7 +373,7 @@ def run_b200(args, rank, world):
                 "zstd3_256k": {"workload": "BASELINE configs[2]: zstd level 3, 256 KiB frames", "value": round(zs_value, 2), "unit": "GB/s",
                                "ms_per_step": round(zs["dev_ms"] / args.steps, 3), "frames": zs["frames"], "compressed_bytes": zs["C"],
                                "roofline": {"bound": "hbm", "achieved": round(zs_ach, 1), "peak": peak, "frac": round(zs_ach / peak, 4),
-                                            "kernel": "zsk_zstd_decode_kernel", "traffic": profile_traffic("zsk_zstd_decode_kernel")},
+                                            "kernel": zs["kernel"], "traffic": profile_traffic(zs["kernel"])},
                                "cpu_baseline": {"value": round(cpu["zstd3"]["gbps"], 3), "unit": "GB/s", "cores": cpu["zstd3"]["threads"],
                                                 "kind": "reference", "one_thread": round(cpu["zstd3"]["gbps_1t"], 3)}},
                 "random_4k": {"workload": f"BASELINE configs[3] shape: {rn['n']} x 4 KiB zseek_pread requests, uniform byte offsets, over the "

@@ -84,6 +84,9 @@ ZSEEK_EXPORT void zseek_b200_cache_clear(zseek_reader_t *reader);
  * kernel in milliseconds (CUDA events on the launching stream; <0 if none). */
 ZSEEK_EXPORT unsigned long long zseek_b200_launch_count(zseek_reader_t *reader);
 ZSEEK_EXPORT double zseek_b200_last_decode_ms(zseek_reader_t *reader);
+/* Name of the decode kernel of that launch (the LZ4 path picks a kernel by the number of frames in the
+ * launch); a static string, "" before the first launch. */
+ZSEEK_EXPORT const char *zseek_b200_last_decode_kernel(zseek_reader_t *reader);
 ZSEEK_EXPORT int zseek_b200_device(zseek_reader_t *reader);
 
 #ifdef __cplusplus

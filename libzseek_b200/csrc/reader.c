@@ -1371,6 +1371,8 @@ double zseek_b200_timer_stop(zseek_reader_t *r)
 
 unsigned long long zseek_b200_launch_count(zseek_reader_t *r) { return r ? zsk_cuda_launch_count(r->cx) : 0; }
 
+const char *zseek_b200_last_decode_kernel(zseek_reader_t *r) { return r ? zsk_cuda_last_decode_kernel(r->cx) : ""; }
+
 double zseek_b200_last_decode_ms(zseek_reader_t *r)
 {
     float ms = -1.0f;

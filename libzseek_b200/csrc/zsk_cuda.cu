@@ -26,6 +26,7 @@ struct zsk_cuda_ctx {
     cudaEvent_t t0, t1;                  /* zsk_cuda_timer_* */
     cudaEvent_t k0, k1;                  /* around the most recent decode kernel */
     int k_valid;
+    const char *k_name;                  /* name of the most recent decode kernel */
     uint32_t *counters;                  /* ZSK_NCOUNTERS work counters, used round-robin */
     unsigned counter_next;
     uint8_t *scratch;                    /* zstd literal scratch for zstd_ctas CTAs */
@@ -312,11 +313,13 @@ int zsk_cuda_launch_decode(zsk_cuda_ctx *cx, int codec, const zsk_decode_args *a
         unsigned ctas = (a.njobs + ZSK_LZ4L_THREADS - 1) / ZSK_LZ4L_THREADS;
         if (ctas > (unsigned)cx->lz4_lane_ctas) ctas = (unsigned)cx->lz4_lane_ctas;
         zsk_lz4_decode_lane_kernel<<<ctas, ZSK_LZ4L_THREADS, ZSK_LZ4L_SMEM, s>>>(a);
+        cx->k_name = "zsk_lz4_decode_lane_kernel";
     } else if (codec == ZSK_CODEC_LZ4) {
         unsigned frames_per_cta = ZSK_LZ4_CTA_THREADS / (unsigned)(cx->lz4_group > 1 ? cx->lz4_group % 100 : 8);
         if (cx->lz4_group == 401) frames_per_cta = ZSK_LZ4_CTA_THREADS / 32;
         unsigned ctas = (a.njobs + frames_per_cta - 1) / frames_per_cta;
         if (ctas > (unsigned)cx->lz4_ctas) ctas = (unsigned)cx->lz4_ctas;
+        cx->k_name = cx->lz4_group == 401 ? "zsk_lz4_decode_batch_kernel" : cx->lz4_group < 100 && cx->lz4_group > 1 ? "zsk_lz4_decode_kernel" : "zsk_lz4_decode_lockstep_kernel";
         switch (cx->lz4_group) {
         case 4: zsk_lz4_decode_kernel<4><<<ctas, ZSK_LZ4_CTA_THREADS, 0, s>>>(a); break;
         case 16: zsk_lz4_decode_kernel<16><<<ctas, ZSK_LZ4_CTA_THREADS, 0, s>>>(a); break;
@@ -330,6 +333,7 @@ int zsk_cuda_launch_decode(zsk_cuda_ctx *cx, int codec, const zsk_decode_args *a
     } else if (codec == ZSK_CODEC_ZSTD) {
         unsigned ctas = a.njobs < (unsigned)cx->zstd_ctas ? a.njobs : (unsigned)cx->zstd_ctas;
         zsk_zstd_decode_kernel<<<ctas, ZSK_ZSTD_CTA_THREADS, 0, s>>>(a);
+        cx->k_name = "zsk_zstd_decode_kernel";
     } else {
         snprintf(cx->err, sizeof(cx->err), "unknown codec %d", codec);
         return -1;
@@ -395,6 +399,8 @@ int zsk_cuda_timer_stop(zsk_cuda_ctx *cx, int stream, float *ms)
     CK(cx, cudaEventElapsedTime(ms, cx->t0, cx->t1));
     return 0;
 }
+
+const char *zsk_cuda_last_decode_kernel(const zsk_cuda_ctx *cx) { return cx->k_name ? cx->k_name : ""; }
 
 int zsk_cuda_last_decode_ms(zsk_cuda_ctx *cx, float *ms)
 {

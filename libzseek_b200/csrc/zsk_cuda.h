@@ -56,6 +56,7 @@ int zsk_cuda_timer_stop(zsk_cuda_ctx *cx, int stream, float *ms); /* synchronise
 /* duration of the most recent decode kernel launched through this context (events around the launch,
  * valid after the stream was synchronised) */
 int zsk_cuda_last_decode_ms(zsk_cuda_ctx *cx, float *ms);
+const char *zsk_cuda_last_decode_kernel(const zsk_cuda_ctx *cx); /* "" before the first launch */
 
 /* diagnostic timeline (ZSEEK_B200_TRACE=1): timestamps of up to ZSK_NTRACE points queued on the streams */
 #define ZSK_NTRACE 192

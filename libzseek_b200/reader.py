@@ -89,6 +89,8 @@ def load_library():
     L.zseek_b200_launch_count.argtypes = [vp]
     L.zseek_b200_last_decode_ms.restype = C.c_double
     L.zseek_b200_last_decode_ms.argtypes = [vp]
+    L.zseek_b200_last_decode_kernel.restype = C.c_char_p
+    L.zseek_b200_last_decode_kernel.argtypes = [vp]
     L.zseek_b200_device.restype = C.c_int
     L.zseek_b200_device.argtypes = [vp]
     _lib = L
@@ -286,6 +288,10 @@ class Reader:
     @property
     def last_decode_ms(self) -> float:
         return float(self.L.zseek_b200_last_decode_ms(self.h))
+
+    @property
+    def last_decode_kernel(self) -> str:
+        return (self.L.zseek_b200_last_decode_kernel(self.h) or b"").decode()
 
     @property
     def device(self) -> int:
