@@ -485,32 +485,75 @@ static __device__ int zsk_zstd_block(zsk_zstd_smem &S, const uint8_t *__restrict
         const uint32_t nchunks = (nseq + ZSK_SEQ_CHUNK - 1) / ZSK_SEQ_CHUNK;
         for (uint32_t c = 0; c <= nchunks; c++) {
             if (warp == 1) {
-                if (lane == 0 && c < nchunks && !st) {
+                if (c < nchunks) {
+                    /* Chunk c in three passes, so that the serial chain (one lane) carries only what is serial:
+                     *   A  lane 0 walks the three FSE states: per sequence it records the states and the bit position,
+                     *      SKIPS the extra bits (their widths come with the table entries) and reads only the state bits;
+                     *   B  all 32 lanes, four sequences each: re-read the entries, fetch the extra bits at the recorded
+                     *      position -> literal length, match length, offset value;
+                     *   C  (warp 0, before it executes the chunk) resolves the repeat-offset codes: a 3-entry history, serial by
+                     *      definition, done by the warp that would otherwise wait for this one at the chunk barrier. */
                     uint32_t (*dstq)[3] = S.seq[c & 1];
                     const uint32_t first = c * ZSK_SEQ_CHUNK;
                     const uint32_t cnt = min(nseq - first, (uint32_t)ZSK_SEQ_CHUNK);
+                    if (lane == 0 && !st) {
+                        for (uint32_t i = 0; i < cnt; i++) {
+                            const uint2 el = S.fse_ll[sl], eo = S.fse_of[so], em = S.fse_ml[sm];
+                            dstq[i][0] = sl | (so << 10) | (sm << 20);
+                            dstq[i][1] = (uint32_t)b.pos;
+                            /* y >> 16 = nbBits | extra bits << 8: the three sums stay inside their bytes (<= 26 and <= 63) */
+                            const uint32_t yl = el.y >> 16, yo = eo.y >> 16, ym = em.y >> 16;
+                            const uint32_t pk = yl + yo + ym;
+                            b.pos -= (int32_t)(pk >> 8);
+                            if (first + i + 1 < nseq) {
+                                /* the state bits of LL, ML, OF are adjacent (LL highest): one field of <= 26 bits, then split */
+                                const uint32_t nm = ym & 0xff, no = yo & 0xff, nb = pk & 0xff;
+                                zsk_bits_ensure(b, (int32_t)nb);
+                                const uint32_t v = zsk_bits_take(b, nb);
+                                so = (eo.y & 0xffff) + (v & ((1u << no) - 1u));
+                                sm = (em.y & 0xffff) + ((v >> no) & ((1u << nm) - 1u));
+                                sl = (el.y & 0xffff) + (v >> (no + nm));
+                            }
+                            if (b.pos < 0) { st = ZSK_ST_BITSTREAM; break; }
+                        }
+                        if (!st && c + 1 == nchunks && b.pos != 0) st = ZSK_ST_BITSTREAM;
+                    }
+                    const int st_a = __shfl_sync(ZSK_FULL, st, 0);
+                    if (!st_a) {
+                        const uint8_t *bits_base = p + S.bs_start;
+                        for (uint32_t i = lane; i < cnt; i += 32) {
+                            const uint32_t ss = dstq[i][0];
+                            const uint2 el = S.fse_ll[ss & 1023u], eo = S.fse_of[(ss >> 10) & 1023u], em = S.fse_ml[ss >> 20];
+                            zsk_bits bb;
+                            bb.base = bits_base;
+                            bb.pos = (int32_t)dstq[i][1];
+                            zsk_bits_refill(bb);                       /* >= 57 bits below pos */
+                            const uint32_t xo = eo.y >> 24, xm = em.y >> 24, xl = el.y >> 24;
+                            const uint32_t ov = eo.x + zsk_bits_take(bb, xo);
+                            zsk_bits_ensure(bb, (int32_t)(xm + xl));
+                            const uint32_t mlen = em.x + zsk_bits_take(bb, xm);
+                            const uint32_t llen = el.x + zsk_bits_take(bb, xl);
+                            dstq[i][0] = llen; dstq[i][1] = mlen; dstq[i][2] = ov;
+                        }
+                    }
+                }
+            } else if (c > 0) {
+                /* warp 0 executes chunk c-1 four sequences per trip: lane group g (8 lanes) takes sequence 4t+g.
+                 * Fast trip (all four): literal run <= 16, match <= 32 and every match source ends before the
+                 * first byte this trip writes -> all loads of the four sequences are in flight together, then
+                 * all stores.  Otherwise the four are executed one after another by the whole warp. */
+                uint32_t (*q)[3] = S.seq[(c - 1) & 1];
+                const uint32_t first = (c - 1) * ZSK_SEQ_CHUNK;
+                const uint32_t cnt = min(nseq - first, (uint32_t)ZSK_SEQ_CHUNK);
+                const unsigned g = lane >> 3, gl = lane & 7;
+                if (lane == 0) { /* pass C: offset value -> offset (repeat-offset history) */
                     uint32_t r0 = S.rep[0], r1 = S.rep[1], r2 = S.rep[2];
                     for (uint32_t i = 0; i < cnt; i++) {
-                        const uint2 el = S.fse_ll[sl], eo = S.fse_of[so], em = S.fse_ml[sm];
-                        /* the window is refilled only when the fields about to be read do not fit what is left of it:
-                         * offset extra (<= 31) + match extra (<= 16), then literal extra (<= 16) + state bits (<= 26) */
-                        const uint32_t xo = eo.y >> 24, xm = em.y >> 24, xl = el.y >> 24;
-                        zsk_bits_ensure(b, (int32_t)(xo + xm));
-                        const uint32_t ov = eo.x + zsk_bits_take(b, xo);
-                        const uint32_t mlen = em.x + zsk_bits_take(b, xm);
-                        const uint32_t nl = (el.y >> 16) & 0xff, nm = (em.y >> 16) & 0xff, no = (eo.y >> 16) & 0xff;
-                        zsk_bits_ensure(b, (int32_t)(xl + nl + nm + no));
-                        const uint32_t llen = el.x + zsk_bits_take(b, xl);
-                        if (first + i + 1 < nseq) {
-                            sl = (el.y & 0xffff) + zsk_bits_take(b, nl);
-                            sm = (em.y & 0xffff) + zsk_bits_take(b, nm);
-                            so = (eo.y & 0xffff) + zsk_bits_take(b, no);
-                        }
-                        if (b.pos < 0) { st = ZSK_ST_BITSTREAM; break; }
+                        const uint32_t ov = q[i][2];
                         uint32_t offset;
                         if (ov > 3) { offset = ov - 3; r2 = r1; r1 = r0; r0 = offset; }
                         else {
-                            const uint32_t idx = ov - 1 + (llen == 0);
+                            const uint32_t idx = ov - 1 + (q[i][0] == 0);
                             if (idx == 0) offset = r0;
                             else {
                                 offset = idx == 1 ? r1 : idx == 2 ? r2 : r0 - 1;
@@ -520,20 +563,14 @@ static __device__ int zsk_zstd_block(zsk_zstd_smem &S, const uint8_t *__restrict
                                 r0 = offset;
                             }
                         }
-                        dstq[i][0] = llen; dstq[i][1] = mlen; dstq[i][2] = offset;
+                        q[i][2] = offset;
                     }
                     S.rep[0] = r0; S.rep[1] = r1; S.rep[2] = r2;
-                    if (!st && c + 1 == nchunks && b.pos != 0) st = ZSK_ST_BITSTREAM;
                 }
-            } else if (c > 0) {
-                /* warp 0 executes chunk c-1 four sequences per trip: lane group g (8 lanes) takes sequence 4t+g.
-                 * Fast trip (all four): literal run <= 16, match <= 32 and every match source ends before the
-                 * first byte this trip writes -> all loads of the four sequences are in flight together, then
-                 * all stores.  Otherwise the four are executed one after another by the whole warp. */
-                const uint32_t (*q)[3] = S.seq[(c - 1) & 1];
-                const uint32_t first = (c - 1) * ZSK_SEQ_CHUNK;
-                const uint32_t cnt = min(nseq - first, (uint32_t)ZSK_SEQ_CHUNK);
-                const unsigned g = lane >> 3, gl = lane & 7;
+                {
+                    const int st_c = __shfl_sync(ZSK_FULL, st, 0);
+                    if (st_c) st = st_c;
+                }
                 for (uint32_t t = 0; t < cnt && !st; t += 4) {
                     const bool act = t + g < cnt;
                     uint32_t llen = 0, mlen = 0, offset = 1;

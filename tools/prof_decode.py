@@ -1,6 +1,6 @@
 """Small driver for profiling one decode kernel under ncu (inputs: reference writer over a zsyn-v1 tile).
 
-    python tools/prof_decode.py lz4|zstd3|zstd19 [size_mib] [iters]
+    python tools/prof_decode.py lz4|zstd3|zstd19|lz4_1m|lz4near [size_mib] [iters] [tile_mib]
 """
 import os
 import sys
@@ -19,6 +19,7 @@ def main():
     kind = sys.argv[1] if len(sys.argv) > 1 else "lz4"
     size = (int(sys.argv[2]) if len(sys.argv) > 2 else 256) << 20
     iters = int(sys.argv[3]) if len(sys.argv) > 3 else 3
+    tile_mib = int(sys.argv[4]) if len(sys.argv) > 4 else 64
     if kind.endswith("near"):
         # diagnostic corpus: same token density as text, but every match source lies within ~600 bytes
         rng = np.random.Generator(np.random.PCG64(5))
@@ -31,7 +32,7 @@ def main():
         tile = arr.tobytes()
         kind = kind[:-4]
     else:
-        tile = zsyn.gen_parallel(min(size, 64 << 20))
+        tile = zsyn.gen_parallel(min(size, tile_mib << 20))
     codec, level, frame = {"lz4": (1, 0, 65536), "zstd3": (0, 3, 262144), "zstd19": (0, 19, 1 << 20), "lz4_1m": (1, 0, 1 << 20)}[kind]
     one = refwriter.write_parallel(tile, codec, level, frame, piece_frames=max(1, (4 << 20) // frame))
     image = refwriter.replicate(one, max(1, size // len(tile)))
