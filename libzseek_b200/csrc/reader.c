@@ -106,10 +106,10 @@ struct zseek_reader {
     uint32_t ra_window, ra_max;
     size_t chunk_bytes; /* decoded bytes per pipeline stage of host-destination range reads */
     size_t ramp_bytes;  /* size of the first pipeline stage; stages double until they reach chunk_bytes */
-    /* launches of at least sort_min LZ4 frames hand the kernel a job list ordered by compressed size (largest
-     * first): the lane-per-frame kernel then runs frames of similar length side by side in a warp, warps retire
-     * as a whole and the longest frames start first.  0 = never. */
-    size_t sort_min;
+    /* launches of at least sort_min LZ4 frames (sort_min_zstd zstd frames) hand the kernel a job list ordered by
+     * compressed size, largest first: the lane-per-frame LZ4 kernel then runs frames of similar length side by
+     * side in a warp, warps retire as a whole, and for both codecs the longest frames start first.  0 = never. */
+    size_t sort_min, sort_min_zstd;
     uint64_t sorted_lo, sorted_hi; /* g_job_ids currently holds the ordered list of [sorted_lo, sorted_hi) */
 
     /* host/device classification of caller buffers, cached per 2 MiB virtual-address block so that the hot
@@ -637,6 +637,7 @@ static zseek_reader_t *reader_open_common(zseek_reader_t *r, size_t cache_size, 
     r->chunk_bytes = env_size("ZSEEK_B200_CHUNK_MB", 512) << 20;
     r->ramp_bytes = env_size("ZSEEK_B200_RAMP_MB", 16) << 20;
     r->sort_min = env_size("ZSEEK_B200_SORT_MIN", 65536);
+    r->sort_min_zstd = env_size("ZSEEK_B200_SORT_MIN_ZSTD", 2048); /* zstd: one CTA per frame, largest frames first trims the last wave */
 
     r->slot_frame = malloc(r->nslots * sizeof(int32_t));
     r->lru_prev = malloc(r->nslots * sizeof(int32_t));
@@ -901,7 +902,7 @@ static bool decode_range_device(zseek_reader_t *r, uint64_t lo, uint64_t hi, uin
     a.first_frame = (uint32_t)lo;
     a.njobs = (uint32_t)(hi - lo);
     a.status = r->g_job_status;
-    if (r->codec == ZSK_CODEC_LZ4 && r->sort_min && hi - lo >= r->sort_min) {
+    if (r->sort_min && hi - lo >= (r->codec == ZSK_CODEC_LZ4 ? r->sort_min : r->sort_min_zstd)) {
         if (r->sorted_lo != lo || r->sorted_hi != hi) {
             order_jobs_by_size(r, lo, hi);
             if (zsk_cuda_memcpy_async(r->cx, r->g_job_ids, r->h_job_ids, (size_t)(hi - lo) * sizeof(uint32_t), ZSK_H2D, ZSK_STREAM_COMPUTE))

@@ -17,7 +17,7 @@
  *   with 32 lanes; warp-level sync only         writes {LL, ML, offset} to smem
  *   ------------------------------ __syncthreads (per chunk) ------------------
  *
- * All tables live in shared memory (Huffman 4 KiB, FSE 10 KiB, two sequence chunks 3 KiB); Huffman
+ * All tables live in shared memory (Huffman 4 KiB, FSE 10 KiB, two sequence chunks 2.25 KiB); Huffman
  * output goes to a per-CTA literal scratch in HBM (L2-resident, <= 128 KiB), the frame's output is
  * written straight to its final place and re-read from L1/L2 for match copies (offsets reach up to
  * the whole frame, far beyond what shared memory could hold for 256 KiB - 1 MiB frames).
@@ -29,7 +29,9 @@
 
 #define ZSK_ZSTD_MAGIC 0xFD2FB528u
 #define ZSK_ZSTD_CTA_THREADS 64
-#define ZSK_SEQ_CHUNK 128
+#ifndef ZSK_SEQ_CHUNK
+#define ZSK_SEQ_CHUNK 96 /* sequences per hand-over between the two warps; 96 keeps the CTA at 18.0 KB of shared memory = 12 CTAs per SM */
+#endif
 #define ZSK_BLOCK_MAX (128u << 10)
 
 struct zsk_zstd_smem {
