@@ -284,6 +284,9 @@ def run_b200(args, rank, world):
             out = torch.empty(n_req * 4096, dtype=torch.uint8, device="cuda")
             rdc = z.Reader(image=pinned, cache_size=rd.frames)       # decoded-frame cache can hold the file
             rdc.load(0, rdc.frames)
+            rdc.pread_batch(offs[:1000], fixed_count=4096, dst=out, dst_stride=4096)  # untimed: one-time buffer allocation
+            rdc.cache_clear()
+            torch.cuda.synchronize()
             t0 = time.perf_counter()
             res = rdc.pread_batch(offs, fixed_count=4096, dst=out, dst_stride=4096)   # cold: decodes every touched frame
             torch.cuda.synchronize()
@@ -296,7 +299,7 @@ def run_b200(args, rank, world):
                 torch.cuda.synchronize()
                 warm.append(time.perf_counter() - t0)
             lat = []
-            for b in range(20):
+            for b in range(100):
                 rdc.cache_clear()
                 t0 = time.perf_counter()
                 rdc.pread_batch(gen_offsets(10000, total, 4096, seed=100 + b), fixed_count=4096, dst=out, dst_stride=4096)
@@ -321,9 +324,12 @@ def run_b200(args, rank, world):
             image, total = inputs[name]
             sample = min(total, (1 << 30) if name == "lz4" else (1 << 30))
             # sample = the first `sample` decompressed bytes of the same file
-            t = cpu_scan(image, sample, threads)
-            t1 = cpu_scan(image, min(sample, 256 << 20), 1, repeats=1)
-            cpu[name] = dict(gbps=sample / t / GB, gbps_1t=min(sample, 256 << 20) / t1 / GB, threads=threads, sample=sample)
+            if world == 1:   # the CPU legs are timed at N = 1 only (other ranks would share the host cores)
+                t = cpu_scan(image, sample, threads)
+                t1 = cpu_scan(image, min(sample, 256 << 20), 1, repeats=1)
+                cpu[name] = dict(gbps=round(sample / t / GB, 3), gbps_1t=round(min(sample, 256 << 20) / t1 / GB, 3), threads=threads, sample=sample)
+            else:
+                cpu[name] = dict(gbps=None, gbps_1t=None, threads=0, sample=sample)
             # correctness spot-check of what was timed on the GPU, against the reference reader
             with RefReader(image) as rr:
                 want = np.frombuffer(rr.pread_full(1 << 20, 0), dtype=np.uint8)
@@ -333,8 +339,11 @@ def run_b200(args, rank, world):
         image, total = inputs["zstd3"]
         r = results["random"]
         n_cpu = min(r["n"], 20000)
-        t, ops = cpu_random(image, r["offs"][:n_cpu], 4096, threads)
-        cpu["random"] = dict(ops=ops / t, threads=threads, n=n_cpu)
+        if world == 1:
+            t, ops = cpu_random(image, r["offs"][:n_cpu], 4096, threads)
+            cpu["random"] = dict(ops=round(ops / t), threads=threads, n=n_cpu)
+        else:
+            cpu["random"] = dict(ops=None, threads=0, n=n_cpu)
         with RefReader(image) as rr:
             for i in range(64):
                 k, b = rr.pread(4096, int(r["offs"][i]))
@@ -366,27 +375,28 @@ def run_b200(args, rank, world):
                          "frac": round(achieved / peak, 4), "traffic": profile_traffic(lz["kernel"]),
                          "kernel": lz["kernel"], "algorithmic_bytes_per_launch": lz["C"] + lz["total"],
                          "peak_source": peak_src},
-            "cpu_baseline": {"value": round(cpu["lz4"]["gbps"], 3), "unit": "GB/s", "cores": cpu["lz4"]["threads"], "kind": "reference",
-                             "sample": f"first {cpu['lz4']['sample'] >> 20} MiB of the same file, one reader per thread, 1 MiB zseek_pread "
-                                       f"requests, cache_size 0, best of 3; 1 thread: {cpu['lz4']['gbps_1t']:.3f} GB/s"},
+            "cpu_baseline": {"value": cpu["lz4"]["gbps"], "unit": "GB/s", "cores": cpu["lz4"]["threads"], "kind": "reference",
+                             "sample": (f"first {cpu['lz4']['sample'] >> 20} MiB of the same file, one reader per thread, 1 MiB zseek_pread "
+                                        f"requests, cache_size 0, best of 3; 1 thread: {cpu['lz4']['gbps_1t']} GB/s") if world == 1 else
+                                       "timed at N = 1 only; see the --impl reference line of this N"},
             "extra": {
                 "zstd3_256k": {"workload": "BASELINE configs[2]: zstd level 3, 256 KiB frames", "value": round(zs_value, 2), "unit": "GB/s",
                                "ms_per_step": round(zs["dev_ms"] / args.steps, 3), "frames": zs["frames"], "compressed_bytes": zs["C"],
                                "roofline": {"bound": "hbm", "achieved": round(zs_ach, 1), "peak": peak, "frac": round(zs_ach / peak, 4),
                                             "kernel": zs["kernel"], "traffic": profile_traffic(zs["kernel"])},
-                               "cpu_baseline": {"value": round(cpu["zstd3"]["gbps"], 3), "unit": "GB/s", "cores": cpu["zstd3"]["threads"],
-                                                "kind": "reference", "one_thread": round(cpu["zstd3"]["gbps_1t"], 3)}},
+                               "cpu_baseline": {"value": cpu["zstd3"]["gbps"], "unit": "GB/s", "cores": cpu["zstd3"]["threads"],
+                                                "kind": "reference", "one_thread": cpu["zstd3"]["gbps_1t"]}},
                 "random_4k": {"workload": f"BASELINE configs[3] shape: {rn['n']} x 4 KiB zseek_pread requests, uniform byte offsets, over the "
                                           f"{zs['total'] >> 30} GiB zstd-3 file (rank 0)",
                               "ops_per_s_cold": round(rn["n"] / rn["cold_s"]), "ops_per_s_warm_cache": round(rn["n"] / rn["warm_s"]),
                               "batch_10k_cold_p50_ms": round(rn["p50_ms"], 3), "batch_10k_cold_p99_ms": round(rn["p99_ms"], 3),
                               "short_reads_at_frame_boundaries": rn["short_reads"],
-                              "cpu_baseline": {"value": round(cpu["random"]["ops"]), "unit": "ops/s", "cores": cpu["random"]["threads"],
+                              "cpu_baseline": {"value": cpu["random"]["ops"], "unit": "ops/s", "cores": cpu["random"]["threads"],
                                                "kind": "reference", "sample": f"first {cpu['random']['n']} requests"}},
                 "wall_s_lz4_timed_region": round(lz["wall"], 4), "kernel_ms_lz4_sum": round(lz["kernel_ms"], 3),
             },
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     barrier()
     cleanup_inputs(cache, rank)
 
@@ -420,8 +430,45 @@ def run_reference(args, rank, world):
             "cpu_baseline": {"value": round(value, 3), "unit": "GB/s", "cores": threads, "kind": "reference", "sample": desc},
             "e2e": {"value": round(value, 3), "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "extra": {"wall_s": round(wall, 3)}}
-    print(json.dumps(line), flush=True)
+    emit(line)
     cleanup_inputs(cache, 0)
+
+
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """Libraries (NCCL prints its version banner) must not write to the stdout the driver parses: fd 1 is pointed
+    at stderr for the whole run and the single JSON line goes to the saved descriptor."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
+def bind_to_gpu_numa_node(local):
+    """N > 1: run this rank (and first-touch its pinned buffers) on the cores next to its GPU."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (w >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            log(f"[bench] local rank {local}: bound to {len(cpus)} cores near GPU {local}")
+    except Exception as e:  # best effort
+        log(f"[bench] local rank {local}: no NUMA binding ({e})")
 
 
 def main():
@@ -436,14 +483,16 @@ def main():
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
+    claim_stdout()
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
     if world > 1:
         import torch
         import torch.distributed as dist
+        bind_to_gpu_numa_node(int(os.environ.get("LOCAL_RANK", 0)))
         torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", 0)))
-        dist.init_process_group("nccl")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ.get("LOCAL_RANK", 0))))
     run_b200(args, rank, world)
     if world > 1:
         import torch.distributed as dist
