@@ -636,7 +636,7 @@ static zseek_reader_t *reader_open_common(zseek_reader_t *r, size_t cache_size, 
     r->mirror_cap = (size_t)r->ra_max * r->max_dsize;
     r->chunk_bytes = env_size("ZSEEK_B200_CHUNK_MB", 512) << 20;
     r->ramp_bytes = env_size("ZSEEK_B200_RAMP_MB", 16) << 20;
-    r->sort_min = env_size("ZSEEK_B200_SORT_MIN", 65536);
+    r->sort_min = env_size("ZSEEK_B200_SORT_MIN", 40960);
     r->sort_min_zstd = env_size("ZSEEK_B200_SORT_MIN_ZSTD", 2048); /* zstd: one CTA per frame, largest frames first trims the last wave */
 
     r->slot_frame = malloc(r->nslots * sizeof(int32_t));

@@ -260,3 +260,93 @@ def test_reference_example_binary_runs_against_b200_reader(flag, tmp_path, torch
     assert "libzseek_b200.so" in needed
     p = subprocess.run([exe, flag, str(src)], capture_output=True, text=True, timeout=600)
     assert p.returncode == 0 and "SUCCESS" in p.stdout, (p.stdout, p.stderr)
+
+
+# --------------------------------------------------------------------------- every LZ4 kernel, whatever the launch size
+LZ4_KERNEL_ENVS = {
+    "lane_per_frame": {"ZSEEK_B200_LZ4_LANE_MIN": "0", "ZSEEK_B200_SORT_MIN": "0"},           # the kernel big launches get
+    "lane_per_frame_ordered_jobs": {"ZSEEK_B200_LZ4_LANE_MIN": "0", "ZSEEK_B200_SORT_MIN": "1"},
+    "warp_per_frame": {"ZSEEK_B200_LZ4_LANE_MIN": "4000000000"},                              # the kernel small launches get
+    "lockstep_groups": {"ZSEEK_B200_LZ4_LANE_MIN": "4000000000", "ZSEEK_B200_LZ4_GROUP": "1"},
+}
+
+
+@pytest.fixture
+def kernel_env(request, monkeypatch):
+    for k, v in request.param.items():
+        monkeypatch.setenv(k, v)      # read by zseek_reader_open* (one device context per reader)
+    return request.param
+
+
+@pytest.mark.parametrize("kernel_env", list(LZ4_KERNEL_ENVS.values()), ids=list(LZ4_KERNEL_ENVS), indirect=True)
+@pytest.mark.parametrize("name", ["tiny_lz4", "zsyn_lz4_64k", "zsyn_lz4_256k_linked", "zsyn_lz4_4k_chunks", "mix_lz4"])
+def test_every_lz4_kernel_matches_golden(lib, golden, name, kernel_env, torch_cuda):
+    """The launch layer picks the LZ4 kernel by the number of frames in the launch; here each one is forced onto the
+    golden files (raw blocks, linked blocks, ragged frames, unaligned frame starts) through whole-file decode to
+    device memory with guard bytes, range reads to host memory and the reference's own read vectors."""
+    torch = torch_cuda
+    cases, _ = golden
+    c = cases[name]
+    total = c["input_len"]
+    with lib.Reader(image=c["image"], cache_size=4) as rd:
+        dev = torch.full((total + 128,), 0xEE, dtype=torch.uint8, device="cuda")
+        for lead in (64, 67):                     # frame outputs 16-byte aligned and not
+            dev.fill_(0xEE)
+            assert rd.decode_frames(0, rd.frames, dev[lead:]) == total
+            got = dev.cpu().numpy()
+            assert hashlib.sha256(got[lead:lead + total].tobytes()).hexdigest() == c["input_sha256"]
+            assert (got[:lead] == 0xEE).all() and (got[lead + total:] == 0xEE).all(), "wrote outside the destination"
+        want_kernel = {"lane": "zsk_lz4_decode_lane_kernel", "warp": "zsk_lz4_decode_batch_kernel", "lock": "zsk_lz4_decode_lockstep_kernel"}
+        key = "lane" if kernel_env.get("ZSEEK_B200_LZ4_LANE_MIN") == "0" else "lock" if "ZSEEK_B200_LZ4_GROUP" in kernel_env else "warp"
+        assert rd.last_decode_kernel == want_kernel[key]
+        assert hashlib.sha256(rd.read_range(total + 5, 0)).hexdigest() == c["input_sha256"]
+        for off, cnt, ret, digest in c["reads"][:120]:
+            r, b = rd.pread(cnt, off)
+            assert r == ret and sha16(b) == digest, (off, cnt)
+
+
+@pytest.mark.parametrize("kernel_env", [LZ4_KERNEL_ENVS["lane_per_frame_ordered_jobs"], LZ4_KERNEL_ENVS["warp_per_frame"]],
+                         ids=["lane_per_frame_ordered_jobs", "warp_per_frame"], indirect=True)
+def test_lz4_kernels_reject_corrupt_frames(lib, golden, kernel_env, torch_cuda):
+    cases, _ = golden
+    c = cases["zsyn_lz4_64k"]
+    with OraclePort(c["image"]) as op:
+        good = op.decode_all()
+        img = bytearray(c["image"])
+        c0, c1 = int(op.c_off[1]), int(op.c_off[2])
+        for k in range(c0 + 20, c1, 97):
+            img[k] ^= 0x55
+        d0, d1 = int(op.d_off[1]), int(op.d_off[2])
+        trunc = bytes(c["image"][:c0 + 100]) + bytes(c1 - c0 - 100) + bytes(c["image"][c1:])   # frame 1 cut short (zeros)
+    for image in (bytes(img), trunc):
+        with lib.Reader(image=image, cache_size=0) as rd:
+            assert rd.pread(100, 0)[1] == good[:100].tobytes()
+            try:
+                b = rd.read_range(d1 - d0, d0)
+                assert len(b) == d1 - d0 and b != good[d0:d1].tobytes()
+            except lib.ZseekError as e:
+                assert str(e).startswith("decompress frame")
+            assert rd.pread(100, d1 + 5)[1] == good[d1 + 5:d1 + 105].tobytes()
+
+
+@pytest.mark.skipif(not have_reference(), reason="oracle/_ref/libzseek_ref.so missing")
+@pytest.mark.parametrize("codec,level,frame", [(LZ4, 0, 65536), (ZSTD, 3, 131072)])
+def test_ordered_job_lists(lib, codec, level, frame, monkeypatch, torch_cuda):
+    """Big launches get a largest-first job list; forced here on a small ragged file: every frame must
+    still land at its own place."""
+    torch = torch_cuda
+    from datagen import refwriter, zsyn
+    monkeypatch.setenv("ZSEEK_B200_SORT_MIN", "1")
+    monkeypatch.setenv("ZSEEK_B200_SORT_MIN_ZSTD", "1")
+    monkeypatch.setenv("ZSEEK_B200_LZ4_LANE_MIN", "0")
+    rng = np.random.Generator(np.random.PCG64(3))
+    data = zsyn.gen(5 << 20, seed=5) + bytes(300000) + rng.integers(0, 256, 400000, dtype=np.uint8).tobytes() + zsyn.gen(1 << 20, seed=6)
+    image = refwriter.write(data, codec, level, frame, 4093)
+    with lib.Reader(image=image, cache_size=0) as rd:
+        dev = torch.full((len(data) + 64,), 0xEE, dtype=torch.uint8, device="cuda")
+        for lo, hi in ((0, rd.frames), (3, rd.frames - 2), (0, rd.frames)):
+            dev.fill_(0xEE)
+            o0, o1 = int(rd.d_off[lo]), int(rd.d_off[hi])
+            assert rd.decode_frames(lo, hi, dev) == o1 - o0
+            got = dev.cpu().numpy()
+            assert got[:o1 - o0].tobytes() == data[o0:o1] and (got[o1 - o0:] == 0xEE).all()
