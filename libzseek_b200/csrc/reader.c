@@ -68,9 +68,14 @@ struct zseek_reader {
     uint8_t *h_stage; /* two halves */
     size_t stage_half;
     int stage_next, stage_inflight;
-    uint8_t *h_mirror; /* decoded bytes of frames [mir_lo, mir_hi) */
+    uint8_t *h_mirror; /* two halves of mirror_cap bytes; half mir_cur holds the decoded bytes of frames [mir_lo, mir_hi) */
     size_t mirror_cap;
     uint64_t mir_lo, mir_hi;
+    int mir_cur;
+    /* asynchronous read-ahead of a sequential host scan: frames [pf_lo, pf_hi) are being decoded into the OTHER half
+     * (everything is queued on the streams; the host has not waited for it yet) */
+    bool pf_active, pf_resident, pf_ok;
+    uint64_t pf_lo, pf_hi;
 
     /* HBM decoded-frame cache */
     size_t user_cache_size;
@@ -119,6 +124,11 @@ struct zseek_reader {
 };
 
 /* ------------------------------------------------------------------ errors (reference src/common.c:45-54) */
+static bool stream_frames_finish(zseek_reader_t *r, uint64_t lo, uint64_t hi, bool resident, bool ok, char *errbuf);
+static void prefetch_drop(zseek_reader_t *r);
+static void prefetch_start(zseek_reader_t *r, void *call_data);
+static uint8_t *mirror_half(zseek_reader_t *r, int which);
+
 static void set_error(char errbuf[ZSEEK_ERRBUF_SIZE], const char *fmt, ...)
 {
     if (!errbuf)
@@ -514,7 +524,7 @@ static bool fill_window(zseek_reader_t *r, uint64_t lo, uint64_t hi, bool mirror
         r->mir_lo = r->mir_hi = 0;
         for (uint64_t f = lo; f < hi; f++) {
             size_t dsz = (size_t)(r->d_off[f + 1] - r->d_off[f]);
-            if (zsk_cuda_memcpy_async(r->cx, r->h_mirror + (r->d_off[f] - r->d_off[lo]), slot_ptr(r, r->frame_slot[f]), dsz,
+            if (zsk_cuda_memcpy_async(r->cx, mirror_half(r, r->mir_cur) + (r->d_off[f] - r->d_off[lo]), slot_ptr(r, r->frame_slot[f]), dsz,
                                       ZSK_D2H, ZSK_STREAM_COMPUTE))
                 return cuda_fail(r, errbuf, "copy frame to host");
         }
@@ -551,6 +561,8 @@ static void reader_free(zseek_reader_t *r)
 {
     if (!r)
         return;
+    if (r->cx)
+        prefetch_drop(r);
     if (r->cx) {
         zsk_cuda_stream_sync(r->cx, ZSK_STREAM_COMPUTE);
         zsk_cuda_stream_sync(r->cx, ZSK_STREAM_H2D);
@@ -665,7 +677,7 @@ static zseek_reader_t *reader_open_common(zseek_reader_t *r, size_t cache_size, 
         zsk_cuda_malloc(r->cx, (void **)&r->g_frame_src, (N + 1) * sizeof(int64_t)) ||
         zsk_cuda_malloc(r->cx, (void **)&r->g_slab, (size_t)r->nslots * r->slot_size + ZSK_PAD_FRONT + ZSK_PAD_BACK) ||
         zsk_cuda_malloc_host(r->cx, (void **)&r->h_stage, r->mem_image ? 1 : 2 * r->stage_half) ||
-        zsk_cuda_malloc_host(r->cx, (void **)&r->h_mirror, r->mirror_cap)) {
+        zsk_cuda_malloc_host(r->cx, (void **)&r->h_mirror, 2 * r->mirror_cap)) {
         set_error(errbuf, "buffer creation failed: %s", zsk_cuda_error(r->cx));
         goto fail;
     }
@@ -741,9 +753,25 @@ static ssize_t pread_locked(zseek_reader_t *r, void *buf, size_t count, size_t o
         return -1;
     int on_device = buf_on_device(r, buf);
     if (!on_device && f >= r->mir_lo && f < r->mir_hi) { /* pinned window hit: plain memcpy */
-        memcpy(buf, r->h_mirror + (offset - r->d_off[r->mir_lo]), n);
+        memcpy(buf, mirror_half(r, r->mir_cur) + (offset - r->d_off[r->mir_lo]), n);
         return (ssize_t)n;
     }
+    if (!on_device && r->pf_active && f == r->pf_lo) {
+        /* the scan reached the window that was being decoded behind its back: wait for it, swap halves, and queue
+         * the window after it before copying this call's bytes */
+        r->pf_active = false;
+        if (stream_frames_finish(r, r->pf_lo, r->pf_hi, r->pf_resident, r->pf_ok, errbuf)) {
+            r->mir_cur ^= 1;
+            r->mir_lo = r->pf_lo;
+            r->mir_hi = r->pf_hi;
+            r->ra_next = r->pf_hi;
+            prefetch_start(r, call_data);
+            memcpy(buf, mirror_half(r, r->mir_cur) + (offset - r->d_off[r->mir_lo]), n);
+            return (ssize_t)n;
+        }
+        /* fall through: decode synchronously and report what fails */
+    }
+    prefetch_drop(r);
     int32_t s = cache_find(r, f);
     if (s < 0) {
         /* miss: decode a window of frames in one launch; the window grows while the access pattern
@@ -757,15 +785,17 @@ static ssize_t pread_locked(zseek_reader_t *r, void *buf, size_t count, size_t o
             /* sequential host reader: decode the window through the H2D / decode / D2H pipeline straight into
              * the pinned mirror (one contiguous copy per chunk); later reads of the window are memcpys */
             r->mir_lo = r->mir_hi = 0;
-            if (!stream_frames_to_host(r, f, hi, r->h_mirror, call_data, errbuf))
+            if (!stream_frames_to_host(r, f, hi, mirror_half(r, r->mir_cur), call_data, errbuf))
                 return -1;
             r->mir_lo = f;
             r->mir_hi = hi;
+            r->ra_next = hi;
+            prefetch_start(r, call_data);
         } else if (!fill_window(r, f, hi, !on_device, call_data, errbuf))
             return -1;
-        r->ra_next = hi;
+        r->ra_next = MAX(hi, r->pf_active ? r->pf_lo : hi);
         if (!on_device) {
-            memcpy(buf, r->h_mirror + (offset - r->d_off[r->mir_lo]), n);
+            memcpy(buf, mirror_half(r, r->mir_cur) + (offset - r->d_off[r->mir_lo]), n);
             return (ssize_t)n;
         }
         s = r->frame_slot[f];
@@ -821,7 +851,7 @@ bool zseek_reader_stats(zseek_reader_t *reader, zseek_reader_stats_t *stats, cha
     stats->decompressed_size = (size_t)reader->d_off[reader->nframes];
     stats->cache_memory = (size_t)reader->cached * reader->slot_size;
     stats->cached_frames = reader->cached;
-    stats->buffer_size = reader->g_comp_cap + (reader->mem_image ? 0 : 2 * reader->stage_half) + reader->mirror_cap;
+    stats->buffer_size = reader->g_comp_cap + (reader->mem_image ? 0 : 2 * reader->stage_half) + 2 * reader->mirror_cap;
     pthread_mutex_unlock(&reader->lock);
     return true;
 }
@@ -834,6 +864,7 @@ bool zseek_b200_set_shard(zseek_reader_t *r, unsigned rank, unsigned world, char
         return false;
     }
     pthread_mutex_lock(&r->lock);
+    prefetch_drop(r);
     r->shard_lo = r->nframes * rank / world;
     r->shard_hi = r->nframes * (rank + 1) / world;
     pthread_mutex_unlock(&r->lock);
@@ -867,6 +898,7 @@ bool zseek_b200_load(zseek_reader_t *r, size_t lo, size_t hi, void *call_data, c
         return false;
     }
     pthread_mutex_lock(&r->lock);
+    prefetch_drop(r);
     bool ok = ensure_resident(r, lo, hi, call_data, errbuf) && (zsk_cuda_stream_sync(r->cx, ZSK_STREAM_H2D) == 0);
     pthread_mutex_unlock(&r->lock);
     return ok;
@@ -925,6 +957,7 @@ ssize_t zseek_b200_decode_frames(zseek_reader_t *r, size_t lo, size_t hi, void *
         return -1;
     }
     pthread_mutex_lock(&r->lock);
+    prefetch_drop(r);
     ssize_t ret = -1;
     if (lo == hi)
         ret = 0;
@@ -1017,7 +1050,10 @@ enum { EV_H2D0 = 0, EV_H2D1 = 1, EV_DEC0 = 2, EV_DEC1 = 3, EV_D2H0 = 4, EV_D2H1 
  * The host only queues work; chunks are ordered by events, so PCIe runs in both directions while
  * the kernel of the next chunk executes.
  */
-static bool stream_frames_to_host(zseek_reader_t *r, uint64_t lo, uint64_t hi, uint8_t *dst, void *call_data, char *errbuf)
+/* Queues the whole pipeline; returns without waiting for the device.  *was_resident tells stream_frames_finish
+ * whether the compressed image was already in HBM. */
+static bool stream_frames_begin(zseek_reader_t *r, uint64_t lo, uint64_t hi, uint8_t *dst, void *call_data, char *errbuf,
+                                bool *was_resident)
 {
     const uint64_t nfr = hi - lo;
     const bool resident = lo >= r->res_lo && hi <= r->res_hi;
@@ -1098,8 +1134,17 @@ static bool stream_frames_to_host(zseek_reader_t *r, uint64_t lo, uint64_t hi, u
         k++;
     }
 #undef CHUNK_END
+    *was_resident = resident;
+    return ok;
+}
+
+/* Waits for a pipeline queued by stream_frames_begin (ok = what begin returned) and checks the frame statuses. */
+static bool stream_frames_finish(zseek_reader_t *r, uint64_t lo, uint64_t hi, bool resident, bool ok, char *errbuf)
+{
     if (ok)
-        ok = finish_decode(r, (uint32_t)nfr, errbuf);
+        ok = finish_decode(r, (uint32_t)(hi - lo), errbuf);
+    else
+        zsk_cuda_stream_sync(r->cx, ZSK_STREAM_COMPUTE);
     if (zsk_cuda_stream_sync(r->cx, ZSK_STREAM_D2H) && ok)
         ok = cuda_fail(r, errbuf, "copy to host");
     zsk_cuda_trace_dump(r->cx);
@@ -1112,6 +1157,41 @@ static bool stream_frames_to_host(zseek_reader_t *r, uint64_t lo, uint64_t hi, u
         r->res_hi = hi;
     }
     return ok;
+}
+
+static bool stream_frames_to_host(zseek_reader_t *r, uint64_t lo, uint64_t hi, uint8_t *dst, void *call_data, char *errbuf)
+{
+    bool resident = false;
+    bool ok = stream_frames_begin(r, lo, hi, dst, call_data, errbuf, &resident);
+    return stream_frames_finish(r, lo, hi, resident, ok, errbuf);
+}
+
+/* ---- asynchronous read-ahead of the plain zseek_pread path */
+static uint8_t *mirror_half(zseek_reader_t *r, int which) { return r->h_mirror + (size_t)which * r->mirror_cap; }
+
+/* Waits for the queued read-ahead (if any) and forgets it: every path that uses the streams, the staging buffers or the
+ * job buffers calls this first. */
+static void prefetch_drop(zseek_reader_t *r)
+{
+    if (!r->pf_active)
+        return;
+    char scratch[ZSEEK_ERRBUF_SIZE];
+    stream_frames_finish(r, r->pf_lo, r->pf_hi, r->pf_resident, r->pf_ok, scratch);
+    r->pf_active = false;
+}
+
+/* Queues the decode of the window after the current one into the other mirror half. */
+static void prefetch_start(zseek_reader_t *r, void *call_data)
+{
+    if (r->pf_active || r->mir_hi <= r->mir_lo || r->mir_hi >= r->shard_hi || r->mir_hi - r->mir_lo < 4)
+        return;
+    r->ra_window = MIN(r->ra_window * 4, r->ra_max);
+    uint64_t lo = r->mir_hi, hi = MIN(lo + r->ra_window, r->shard_hi);
+    char scratch[ZSEEK_ERRBUF_SIZE]; /* a failing read-ahead is not an error of this call: the window is retried synchronously */
+    r->pf_ok = stream_frames_begin(r, lo, hi, mirror_half(r, r->mir_cur ^ 1), call_data, scratch, &r->pf_resident);
+    r->pf_lo = lo;
+    r->pf_hi = hi;
+    r->pf_active = true;
 }
 
 /* one partial frame piece -> host memory (through the decoded-frame cache) */
@@ -1169,6 +1249,7 @@ ssize_t zseek_b200_read_range(zseek_reader_t *r, void *buf, size_t count, size_t
         return -1;
     }
     pthread_mutex_lock(&r->lock);
+    prefetch_drop(r);
     ssize_t ret = -1;
     size_t total = (size_t)r->d_off[r->nframes];
     if (offset >= total || count == 0) {
@@ -1242,6 +1323,7 @@ ssize_t zseek_b200_pread_batch(zseek_reader_t *r, size_t n, const uint64_t *offs
         return -1;
     }
     pthread_mutex_lock(&r->lock);
+    prefetch_drop(r);
     ssize_t ret = -1;
     uint64_t N = r->nframes;
     int on_device = buf_on_device(r, dst);
@@ -1346,6 +1428,7 @@ void zseek_b200_cache_clear(zseek_reader_t *r)
     if (!r)
         return;
     pthread_mutex_lock(&r->lock);
+    prefetch_drop(r);
     cache_clear(r);
     pthread_mutex_unlock(&r->lock);
 }
@@ -1355,6 +1438,7 @@ void zseek_b200_unload(zseek_reader_t *r)
     if (!r)
         return;
     pthread_mutex_lock(&r->lock);
+    prefetch_drop(r);
     zsk_cuda_stream_sync(r->cx, ZSK_STREAM_COMPUTE);
     r->res_lo = r->res_hi = 0;
     pthread_mutex_unlock(&r->lock);
