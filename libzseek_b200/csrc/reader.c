@@ -85,6 +85,7 @@ struct zseek_reader {
     int32_t *slot_frame, *lru_prev, *lru_next;
     int32_t lru_head, lru_tail; /* head = MRU */
     int32_t *frame_slot;        /* [N] */
+    uint32_t *valid_len;        /* [N] decoded bytes of a cached frame that are valid (a batch may decode only a prefix) */
     uint32_t cached;
     int64_t *g_frame_src;       /* device [N]: byte offset of frame in slab data area, -1 absent */
     int64_t *h_frame_src;       /* host copy being edited */
@@ -94,6 +95,7 @@ struct zseek_reader {
     uint32_t job_cap;
     uint32_t *g_job_ids, *h_job_ids;
     uint64_t *g_job_offs, *h_job_offs;
+    uint32_t *g_job_limits, *h_job_limits;
     int32_t *g_job_status, *h_job_status;
 
     /* batch scratch (device), capacity batch_cap requests */
@@ -115,6 +117,7 @@ struct zseek_reader {
      * compressed size, largest first: the lane-per-frame LZ4 kernel then runs frames of similar length side by
      * side in a warp, warps retire as a whole, and for both codecs the longest frames start first.  0 = never. */
     size_t sort_min, sort_min_zstd;
+    bool partial_decode; /* batches decode a missing frame only up to the last byte they need of it (ZSEEK_B200_PARTIAL=0: whole frames) */
     uint64_t sorted_lo, sorted_hi; /* g_job_ids currently holds the ordered list of [sorted_lo, sorted_hi) */
 
     /* host/device classification of caller buffers, cached per 2 MiB virtual-address block so that the hot
@@ -306,9 +309,17 @@ static void lru_push_front(zseek_reader_t *r, int32_t s)
 
 static uint8_t *slot_ptr(zseek_reader_t *r, int32_t s) { return r->g_slab + ZSK_PAD_FRONT + (size_t)s * r->slot_size; }
 
-static int32_t cache_find(zseek_reader_t *r, uint64_t f)
+static void cache_drop_slot(zseek_reader_t *r, int32_t s);
+
+/* slot of frame f if at least its first `need` bytes are decoded there (a batch may have decoded only a prefix);
+ * a shorter entry is dropped and reported as a miss */
+static int32_t cache_find_prefix(zseek_reader_t *r, uint64_t f, uint32_t need)
 {
     int32_t s = r->frame_slot[f];
+    if (s >= 0 && r->valid_len[f] < need) {
+        cache_drop_slot(r, s);
+        return -1;
+    }
     if (s >= 0 && r->lru_head != s) { /* promote to MRU */
         lru_unlink(r, s);
         lru_push_front(r, s);
@@ -316,11 +327,18 @@ static int32_t cache_find(zseek_reader_t *r, uint64_t f)
     return s;
 }
 
+/* slot of the completely decoded frame f, or -1 */
+static int32_t cache_find(zseek_reader_t *r, uint64_t f)
+{
+    return cache_find_prefix(r, f, (uint32_t)(r->d_off[f + 1] - r->d_off[f]));
+}
+
 static void cache_drop_slot(zseek_reader_t *r, int32_t s)
 {
     int32_t f = r->slot_frame[s];
     if (f >= 0) {
         r->frame_slot[f] = -1;
+        r->valid_len[f] = 0;
         r->h_frame_src[f] = -1;
         r->slot_frame[s] = -1;
         r->cached--;
@@ -443,14 +461,18 @@ static bool ensure_jobs(zseek_reader_t *r, uint32_t n, char *errbuf)
     uint32_t cap = MAX(n, 1024u);
     zsk_cuda_stream_sync(r->cx, ZSK_STREAM_COMPUTE);
     zsk_cuda_free(r->cx, r->g_job_ids); zsk_cuda_free(r->cx, r->g_job_offs); zsk_cuda_free(r->cx, r->g_job_status);
+    zsk_cuda_free(r->cx, r->g_job_limits);
     zsk_cuda_free_host(r->cx, r->h_job_ids); zsk_cuda_free_host(r->cx, r->h_job_offs); zsk_cuda_free_host(r->cx, r->h_job_status);
-    r->g_job_ids = NULL; r->g_job_offs = NULL; r->g_job_status = NULL;
-    r->h_job_ids = NULL; r->h_job_offs = NULL; r->h_job_status = NULL;
+    zsk_cuda_free_host(r->cx, r->h_job_limits);
+    r->g_job_ids = NULL; r->g_job_offs = NULL; r->g_job_status = NULL; r->g_job_limits = NULL;
+    r->h_job_ids = NULL; r->h_job_offs = NULL; r->h_job_status = NULL; r->h_job_limits = NULL;
     r->job_cap = 0;
     r->sorted_lo = r->sorted_hi = 0;
     if (zsk_cuda_malloc(r->cx, (void **)&r->g_job_ids, cap * sizeof(uint32_t)) ||
         zsk_cuda_malloc(r->cx, (void **)&r->g_job_offs, cap * sizeof(uint64_t)) ||
         zsk_cuda_malloc(r->cx, (void **)&r->g_job_status, cap * sizeof(int32_t)) ||
+        zsk_cuda_malloc(r->cx, (void **)&r->g_job_limits, cap * sizeof(uint32_t)) ||
+        zsk_cuda_malloc_host(r->cx, (void **)&r->h_job_limits, cap * sizeof(uint32_t)) ||
         zsk_cuda_malloc_host(r->cx, (void **)&r->h_job_ids, cap * sizeof(uint32_t)) ||
         zsk_cuda_malloc_host(r->cx, (void **)&r->h_job_offs, cap * sizeof(uint64_t)) ||
         zsk_cuda_malloc_host(r->cx, (void **)&r->h_job_status, cap * sizeof(int32_t)))
@@ -473,15 +495,18 @@ static bool finish_decode(zseek_reader_t *r, uint32_t njobs, char *errbuf)
     return true;
 }
 
-/* Decodes the frames listed in h_job_ids[0..n) (not cached yet) into freshly taken cache slots. */
-static bool decode_into_cache(zseek_reader_t *r, uint32_t n, char *errbuf)
+/* Decodes the frames listed in h_job_ids[0..n) (not cached yet) into freshly taken cache slots.  need != NULL: frame f
+ * is only needed up to byte need[f]; the kernels may stop there (the slot then holds a valid prefix). */
+static bool decode_into_cache(zseek_reader_t *r, uint32_t n, const uint32_t *need, char *errbuf)
 {
     if (n == 0)
         return true;
     r->sorted_lo = r->sorted_hi = 0; /* the job list is about to be overwritten */
     for (uint32_t i = 0; i < n; i++) {
-        int32_t s = cache_take(r, r->h_job_ids[i]);
+        const uint32_t f = r->h_job_ids[i];
+        int32_t s = cache_take(r, f);
         r->h_job_offs[i] = (uint64_t)((size_t)s * r->slot_size);
+        r->h_job_limits[i] = need ? need[f] : 0xffffffffu;
     }
     zsk_decode_args a;
     fill_decode_args(r, &a);
@@ -490,16 +515,22 @@ static bool decode_into_cache(zseek_reader_t *r, uint32_t n, char *errbuf)
     a.dst = r->g_slab + ZSK_PAD_FRONT;
     a.njobs = n;
     a.status = r->g_job_status;
+    a.limits = need ? r->g_job_limits : NULL;
     bool ok = !zsk_cuda_memcpy_async(r->cx, r->g_job_ids, r->h_job_ids, n * sizeof(uint32_t), ZSK_H2D, ZSK_STREAM_COMPUTE) &&
               !zsk_cuda_memcpy_async(r->cx, r->g_job_offs, r->h_job_offs, n * sizeof(uint64_t), ZSK_H2D, ZSK_STREAM_COMPUTE) &&
+              (!need || !zsk_cuda_memcpy_async(r->cx, r->g_job_limits, r->h_job_limits, n * sizeof(uint32_t), ZSK_H2D, ZSK_STREAM_COMPUTE)) &&
               !zsk_cuda_launch_decode(r->cx, r->codec, &a, ZSK_STREAM_COMPUTE);
     if (!ok)
         cuda_fail(r, errbuf, "decompress frame");
     else
         ok = finish_decode(r, n, errbuf);
-    if (!ok) /* never leave undecoded slots marked valid */
-        for (uint32_t i = 0; i < n; i++)
-            cache_drop_slot(r, r->frame_slot[r->h_job_ids[i]]);
+    for (uint32_t i = 0; i < n; i++) {
+        const uint32_t f = r->h_job_ids[i];
+        if (!ok) /* never leave undecoded slots marked valid */
+            cache_drop_slot(r, r->frame_slot[f]);
+        else
+            r->valid_len[f] = (uint32_t)MIN((uint64_t)r->h_job_limits[i], r->d_off[f + 1] - r->d_off[f]);
+    }
     return ok;
 }
 
@@ -517,7 +548,7 @@ static bool fill_window(zseek_reader_t *r, uint64_t lo, uint64_t hi, bool mirror
         uint64_t mlo = r->h_job_ids[0], mhi = (uint64_t)r->h_job_ids[n - 1] + 1;
         if (!ensure_resident(r, mlo, mhi, call_data, errbuf))
             return false;
-        if (!decode_into_cache(r, n, errbuf))
+        if (!decode_into_cache(r, n, NULL, errbuf))
             return false;
     }
     if (mirror) {
@@ -567,18 +598,19 @@ static void reader_free(zseek_reader_t *r)
         zsk_cuda_stream_sync(r->cx, ZSK_STREAM_COMPUTE);
         zsk_cuda_stream_sync(r->cx, ZSK_STREAM_H2D);
         zsk_cuda_stream_sync(r->cx, ZSK_STREAM_D2H);
-        void *dev[] = { r->g_coff, r->g_doff, r->g_comp, r->g_slab, r->g_frame_src, r->g_job_ids, r->g_job_offs, r->g_job_status,
+        void *dev[] = { r->g_coff, r->g_doff, r->g_comp, r->g_slab, r->g_frame_src, r->g_job_ids, r->g_job_offs, r->g_job_status, r->g_job_limits,
                         r->g_b_offsets, r->g_b_counts, r->g_b_dstoffs, r->g_b_frame, r->g_b_inframe, r->g_b_nbytes, r->g_touched,
                         r->g_miss_ids, r->g_miss_count, r->g_out };
         for (size_t i = 0; i < sizeof(dev) / sizeof(dev[0]); i++)
             zsk_cuda_free(r->cx, dev[i]);
-        void *pin[] = { r->h_stage, r->h_mirror, r->h_job_ids, r->h_job_offs, r->h_job_status };
+        void *pin[] = { r->h_stage, r->h_mirror, r->h_job_ids, r->h_job_offs, r->h_job_status, r->h_job_limits };
         for (size_t i = 0; i < sizeof(pin) / sizeof(pin[0]); i++)
             zsk_cuda_free_host(r->cx, pin[i]);
         zsk_cuda_ctx_destroy(r->cx);
     }
     free(r->c_off); free(r->d_off);
-    free(r->slot_frame); free(r->lru_prev); free(r->lru_next); free(r->frame_slot); free(r->h_frame_src); free(r->h_touched);
+    free(r->slot_frame); free(r->lru_prev); free(r->lru_next); free(r->frame_slot); free(r->valid_len);
+    free(r->h_frame_src); free(r->h_touched);
     pthread_mutex_destroy(&r->lock);
     free(r);
 }
@@ -649,15 +681,17 @@ static zseek_reader_t *reader_open_common(zseek_reader_t *r, size_t cache_size, 
     r->chunk_bytes = env_size("ZSEEK_B200_CHUNK_MB", 512) << 20;
     r->ramp_bytes = env_size("ZSEEK_B200_RAMP_MB", 16) << 20;
     r->sort_min = env_size("ZSEEK_B200_SORT_MIN", 40960);
+    r->partial_decode = env_size("ZSEEK_B200_PARTIAL", 1) != 0;
     r->sort_min_zstd = env_size("ZSEEK_B200_SORT_MIN_ZSTD", 2048); /* zstd: one CTA per frame, largest frames first trims the last wave */
 
     r->slot_frame = malloc(r->nslots * sizeof(int32_t));
     r->lru_prev = malloc(r->nslots * sizeof(int32_t));
     r->lru_next = malloc(r->nslots * sizeof(int32_t));
     r->frame_slot = malloc((N + 1) * sizeof(int32_t));
+    r->valid_len = calloc(N + 1, sizeof(uint32_t));
     r->h_frame_src = malloc((N + 1) * sizeof(int64_t));
     r->h_touched = malloc((N + 1) * sizeof(uint32_t));
-    if (!r->slot_frame || !r->lru_prev || !r->lru_next || !r->frame_slot || !r->h_frame_src || !r->h_touched) {
+    if (!r->slot_frame || !r->lru_prev || !r->lru_next || !r->frame_slot || !r->valid_len || !r->h_frame_src || !r->h_touched) {
         set_error(errbuf, "cache creation failed");
         goto fail;
     }
@@ -1373,7 +1407,7 @@ ssize_t zseek_b200_pread_batch(zseek_reader_t *r, size_t n, const uint64_t *offs
                 goto out;
             }
             in_group++;
-            if (cache_find(r, f) < 0) { /* hits are promoted to MRU so the takes below cannot evict them */
+            if (cache_find_prefix(r, f, r->h_touched[f]) < 0) { /* hits are promoted to MRU so the takes below cannot evict them */
                 r->h_job_ids[nmiss++] = (uint32_t)f;
                 g_lo = MIN(g_lo, f);
                 g_hi = MAX(g_hi, f + 1);
@@ -1382,7 +1416,7 @@ ssize_t zseek_b200_pread_batch(zseek_reader_t *r, size_t n, const uint64_t *offs
         if (in_group == 0)
             break;
         if (nmiss) {
-            if (!ensure_resident(r, g_lo, g_hi, call_data, errbuf) || !decode_into_cache(r, nmiss, errbuf))
+            if (!ensure_resident(r, g_lo, g_hi, call_data, errbuf) || !decode_into_cache(r, nmiss, r->partial_decode ? r->h_touched : NULL, errbuf))
                 goto out;
         }
         if (!push_frame_src(r, errbuf))

@@ -25,7 +25,8 @@ enum zsk_status {
     ZSK_ST_BITSTREAM = 6,   /* backward bitstream over/under-run */
     ZSK_ST_TABLE = 7,       /* bad FSE / Huffman description */
     ZSK_ST_UNSUPPORTED = 8, /* dictionary id */
-    ZSK_ST_SIZE = 9         /* frame decodes to fewer bytes than the seek table's dSize */
+    ZSK_ST_SIZE = 9,        /* frame decodes to fewer bytes than the seek table's dSize */
+    ZSK_ST_STOPPED = 100    /* kernel-internal: the job's limit was reached (reported as ZSK_ST_OK) */
 };
 
 /* Device buffers handed to the kernels must be readable ZSK_PAD_FRONT bytes before and ZSK_PAD_BACK
@@ -54,6 +55,9 @@ typedef struct zsk_decode_args {
     int32_t *status;            /* [njobs] */
     uint32_t *work_counter;     /* zero-initialised; dynamic job distribution (filled in by the launch layer) */
     uint8_t *scratch;           /* zstd literal scratch, ZSK_LIT_SCRATCH bytes per CTA (filled in by the launch layer) */
+    const uint32_t *limits;     /* optional [njobs]: job i may stop once limits[i] bytes of its frame are decoded (a batch of
+                                 * small reads needs only the prefix of a frame up to its last requested byte, like the
+                                 * reference's streaming no-cache path, src/decompress.c:419-454); NULL = whole frames */
 } zsk_decode_args;
 
 /* K1: batched offset -> frame lookup (semantics of reference src/seek_table.c:187-202 + decompress.c:445) */
@@ -67,7 +71,8 @@ typedef struct zsk_lookup_args {
     int32_t *frame;          /* [n] out: frame index or -1 (EOF) */
     uint32_t *inframe;       /* [n] out */
     uint32_t *nbytes;        /* [n] out: MIN(count, frame_end - offset) */
-    uint32_t *touched;       /* optional [N] flags: set to 1 for every frame some request needs */
+    uint32_t *touched;       /* optional [N], zero-initialised: for every frame some request needs, the largest in-frame end
+                              * offset (inframe + nbytes, at least 1) over the batch */
 } zsk_lookup_args;
 
 /* K4: per-request range copy out of decoded frames */

@@ -427,7 +427,7 @@ __global__ void __launch_bounds__(ZSK_LZ4_CTA_THREADS) zsk_lz4_decode_batch_kern
     int state = ZSK_LZ4_W_FETCH;
     const uint8_t *src = nullptr;
     uint8_t *out = nullptr;
-    uint32_t n = 0, ip = 0, bend = 0, op = 0, cap = 0, job = 0, flags = 0, max_block = 0;
+    uint32_t n = 0, ip = 0, bend = 0, op = 0, cap = 0, job = 0, flags = 0, max_block = 0, stop = 0xffffffffu;
     uint64_t content_size = 0;
     for (;;) {
         __syncwarp(); /* orders the previous trip's stores before this trip's loads */
@@ -581,6 +581,7 @@ __global__ void __launch_bounds__(ZSK_LZ4_CTA_THREADS) zsk_lz4_decode_batch_kern
                     }
                 }
             }
+            if (!st && op >= stop) frame_end = true; /* the caller needs no byte beyond `stop` of this frame */
         } else if (state == ZSK_LZ4_W_BLOCK) {
             if (bend && (flags & 16)) { /* block checksum after the compressed block just finished */
                 if (n - ip < 4) st = ZSK_ST_TRUNC; else ip += 4;
@@ -607,6 +608,7 @@ __global__ void __launch_bounds__(ZSK_LZ4_CTA_THREADS) zsk_lz4_decode_batch_kern
                             op += bs;
                             ip += bs;
                             if (flags & 16) { if (n - ip < 4) st = ZSK_ST_TRUNC; else ip += 4; }
+                            if (!st && op >= stop) frame_end = true;
                         }
                     } else if (bs == 0) {
                         st = ZSK_ST_FORMAT;
@@ -628,6 +630,7 @@ __global__ void __launch_bounds__(ZSK_LZ4_CTA_THREADS) zsk_lz4_decode_batch_kern
             n = (uint32_t)(c1 - c0);
             op = 0;
             bend = 0;
+            stop = a.limits ? a.limits[job] : 0xffffffffu;
             if (n < 7) st = ZSK_ST_TRUNC;
             else if (zsk_rd32(src) != ZSK_LZ4_MAGIC) st = ZSK_ST_MAGIC;
             else {

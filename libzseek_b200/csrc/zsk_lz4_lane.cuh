@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(ZSK_LZ4L_THREADS) zsk_lz4_decode_lane_kernel(z
     uint32_t n = 0, ip = 0, bend = 0, opp = 0, cap = 0, job = 0, flags = 0, max_block = 0;
     uint32_t sal = 0, oal = 0;    /* misalignment of src inside its 16-byte chunk / of out inside its 32-byte sector */
     uint32_t fx = 0, fhist = 0;   /* input ring refills issued up to fx (ip + sal coordinates); refill flags of the last DEPTH trips */
-    uint32_t lrem = 0, mrem = 0, moff = 0, moffe = 0, mnib = 0, drain = 0;
+    uint32_t lrem = 0, mrem = 0, moff = 0, moffe = 0, mnib = 0, drain = 0, stop = 0xffffffffu;
     uint64_t content_size = 0;
     /* executor state */
     uint32_t ope = 0, flushed = 0; /* decoded bytes [0, ope) are in the ring or in global memory, [0, flushed) in global memory */
@@ -200,7 +200,9 @@ __global__ void __launch_bounds__(ZSK_LZ4L_THREADS) zsk_lz4_decode_lane_kernel(z
 
         /* ---- 3. phase machine: decide this trip's micro-op */
         uint32_t nlit = 0, lpos = 0, mlen = 0, muse = 0;
-        if (ready) {
+        if (streaming && opp >= stop) {
+            frame_end = true; /* the caller needs no byte beyond `stop` of this frame: close it as if the EndMark had come */
+        } else if (ready) {
             if (phase == ZSK_L_TOKEN) {
                 const uint32_t tok = a0 & 0xffu, L = tok >> 4, M = tok & 15u;
                 if (ip >= bend) {
@@ -448,6 +450,7 @@ __global__ void __launch_bounds__(ZSK_LZ4L_THREADS) zsk_lz4_decode_lane_kernel(z
                 n = (uint32_t)(c1 - c0);
                 opp = 0;
                 bend = 0;
+                stop = a.limits ? a.limits[job] : 0xffffffffu;
                 int hs = ZSK_ST_OK;
                 if (n < 7) hs = ZSK_ST_TRUNC;
                 else if (zsk_rd32(src) != ZSK_LZ4_MAGIC) hs = ZSK_ST_MAGIC;

@@ -8,6 +8,7 @@
  *     frame   = largest i in [0,N) with d_off[i] <= offset, or -1 when offset >= d_off[N]   (B2, B4)
  *     inframe = offset - d_off[frame]
  *     nbytes  = MIN(count, d_off[frame+1] - offset)   — a read never crosses a frame boundary (B1, B3)
+ * and, per frame, touched[frame] = the largest inframe + nbytes any request of the batch reaches (>= 1 when touched).
  *
  * K4 replaces the memcpy out of the cached frame (reference src/decompress.c:558,788): one warp per
  * request copies nbytes from the decoded frame (HBM frame cache slot) to the caller's buffer with
@@ -39,7 +40,7 @@ __global__ void __launch_bounds__(256) zsk_lookup_kernel(zsk_lookup_args a)
             inframe = (uint32_t)(off - d0);
             const uint64_t room = d1 - off;
             nb = (uint32_t)(cnt < room ? cnt : room);
-            if (a.touched) a.touched[f] = 1;
+            if (a.touched) atomicMax(&a.touched[f], max(1u, inframe + nb)); /* how much of the frame this batch needs */
         }
         a.frame[i] = (int32_t)f;
         a.inframe[i] = inframe;

@@ -346,7 +346,7 @@ static __device__ __forceinline__ void zsk_warp_literals(uint8_t *dst, const zsk
  * identical arguments; returns the (CTA-uniform) status.  *pop is advanced by the block's output.
  */
 static __device__ int zsk_zstd_block(zsk_zstd_smem &S, const uint8_t *__restrict__ p, uint32_t n, uint8_t *out, uint32_t *pop,
-                                     uint32_t cap, uint8_t *lit_scratch)
+                                     uint32_t cap, uint8_t *lit_scratch, uint32_t stop)
 {
     const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     /* ---------------- literals section header (uniform) */
@@ -625,6 +625,7 @@ static __device__ int zsk_zstd_block(zsk_zstd_smem &S, const uint8_t *__restrict
                         }
                     }
                 }
+                if (!st && op >= stop) st = ZSK_ST_STOPPED; /* the caller needs no byte beyond `stop` of this frame */
             }
             if ((st = zsk_cta_status(S, st))) return st;
         }
@@ -645,7 +646,7 @@ static __device__ int zsk_zstd_block(zsk_zstd_smem &S, const uint8_t *__restrict
 
 /* One complete zstd frame; all CTA threads call with identical arguments. */
 static __device__ int zsk_zstd_frame(zsk_zstd_smem &S, const uint8_t *__restrict__ src, uint32_t n, uint8_t *out, uint32_t cap,
-                                     uint32_t *produced, uint8_t *lit_scratch)
+                                     uint32_t *produced, uint8_t *lit_scratch, uint32_t stop)
 {
     const unsigned tid = threadIdx.x;
     if (n < 6) return ZSK_ST_TRUNC;
@@ -695,12 +696,13 @@ static __device__ int zsk_zstd_frame(zsk_zstd_smem &S, const uint8_t *__restrict
         } else if (type == 2) {
             if (bsize > n - ip) return ZSK_ST_TRUNC;
             if (bsize > ZSK_BLOCK_MAX) return ZSK_ST_FORMAT;
-            int st = zsk_zstd_block(S, src + ip, bsize, out, &op, cap, lit_scratch);
+            int st = zsk_zstd_block(S, src + ip, bsize, out, &op, cap, lit_scratch, stop);
             if (st) return st;
             ip += bsize;
         } else return ZSK_ST_FORMAT;
         __syncthreads(); /* this block's output is visible to whoever reads it as match source next */
         if (last) break;
+        if (op >= stop) return ZSK_ST_STOPPED;
     }
     if (cksum && n - ip < 4) return ZSK_ST_TRUNC;
     if (fcs_sz && fcs != op) return ZSK_ST_FORMAT;
@@ -724,8 +726,10 @@ __global__ void __launch_bounds__(ZSK_ZSTD_CTA_THREADS) zsk_zstd_decode_kernel(z
         uint8_t *out = a.dst + (a.dst_offs ? a.dst_offs[job] : d0 - a.dst_base);
         const uint32_t cap = (uint32_t)(d1 - d0);
         uint32_t produced = 0;
-        int st = zsk_zstd_frame(S, src, (uint32_t)(c1 - c0), out, cap, &produced, lit_scratch);
-        if (st == ZSK_ST_OK && produced != cap) st = ZSK_ST_SIZE;
+        const uint32_t stop = a.limits ? a.limits[job] : 0xffffffffu;
+        int st = zsk_zstd_frame(S, src, (uint32_t)(c1 - c0), out, cap, &produced, lit_scratch, stop);
+        if (st == ZSK_ST_STOPPED) st = ZSK_ST_OK;
+        else if (st == ZSK_ST_OK && produced != cap) st = ZSK_ST_SIZE;
         if (threadIdx.x == 0) a.status[job] = st;
     }
 }

@@ -15,14 +15,14 @@ extern "C" {
 __attribute__((visibility("default")))
 void emu_decode(int codec, const uint8_t *comp, uint64_t comp_base, const uint64_t *c_off, const uint64_t *d_off,
                 const uint32_t *frame_ids, const uint64_t *dst_offs, uint8_t *dst, uint64_t dst_base,
-                uint32_t first_frame, uint32_t njobs, int32_t *status, uint32_t ctas)
+                uint32_t first_frame, uint32_t njobs, int32_t *status, uint32_t ctas, const uint32_t *limits)
 {
     uint32_t counter = 0;
     std::vector<uint8_t> scratch((size_t)ctas * ZSK_LIT_SCRATCH + 64);
     zsk_decode_args a;
     a.c_off = c_off; a.d_off = d_off; a.comp = comp; a.comp_base = comp_base; a.frame_ids = frame_ids;
     a.dst_offs = dst_offs; a.dst = dst; a.dst_base = dst_base; a.first_frame = first_frame; a.njobs = njobs;
-    a.status = status; a.work_counter = &counter; a.scratch = scratch.data();
+    a.status = status; a.work_counter = &counter; a.scratch = scratch.data(); a.limits = limits;
     if (codec == 1) emu::launch(dim3(ctas), dim3(ZSK_LZ4_CTA_THREADS), 0, [&] { zsk_lz4_decode_batch_kernel(a); });           /* shipped default */
     else if (codec == 101) emu::launch(dim3(ctas), dim3(ZSK_LZ4_CTA_THREADS), 0, [&] { zsk_lz4_decode_lockstep_kernel<8>(a); }); /* alternative */
     else if (codec == 102) emu::launch(dim3(ctas), dim3(ZSK_LZ4L_THREADS), ZSK_LZ4L_SMEM, [&] { zsk_lz4_decode_lane_kernel(a); });  /* many-frame launches */

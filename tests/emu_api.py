@@ -15,7 +15,7 @@ def lib():
     subprocess.run(["make", "-C", EMU_DIR, "-s"], check=True)
     L = C.CDLL(EMU_SO)
     L.emu_decode.argtypes = [C.c_int, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
-                             C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32]
+                             C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p]
     L.emu_lookup.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p,
                              C.c_void_p, C.c_void_p, C.c_void_p]
     L.emu_gather.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
@@ -23,7 +23,7 @@ def lib():
     return L
 
 
-def decode_all(L, image: bytes, codec: int, c_off: np.ndarray, d_off: np.ndarray, ctas: int = 3, misalign: int = 0):
+def decode_all(L, image: bytes, codec: int, c_off: np.ndarray, d_off: np.ndarray, ctas: int = 3, misalign: int = 0, limits=None):
     """Whole-file decode with the emulated K2/K3; returns (decoded bytes, status array)."""
     n = len(c_off) - 1
     payload = int(c_off[-1])
@@ -37,7 +37,7 @@ def decode_all(L, image: bytes, codec: int, c_off: np.ndarray, d_off: np.ndarray
     c_off = np.ascontiguousarray(c_off, dtype=np.uint64)
     d_off = np.ascontiguousarray(d_off, dtype=np.uint64)
     L.emu_decode(codec, comp.ctypes.data + FRONT_PAD, 0, c_off.ctypes.data, d_off.ctypes.data, None, None,
-                 dst.ctypes.data, 0, 0, n, status.ctypes.data, ctas)
+                 dst.ctypes.data, 0, 0, n, status.ctypes.data, ctas, limits.ctypes.data if limits is not None else None)
     assert (dst[total:] == 0xEE).all(), "emulated kernel wrote past the end of the output"
     assert (raw[:lead] == 0xEE).all(), "emulated kernel wrote before the start of the output"
     return dst[:total], status[:n]

@@ -153,3 +153,25 @@ def test_emulated_lane_lz4_kernel_sequence_shapes(emu, kw):
             out, status = emu_api.decode_all(emu, image, codec, op.c_off, op.d_off, ctas=1, misalign=mis)
             assert (status == 0).all(), status
             assert out.tobytes() == data
+
+
+@pytest.mark.parametrize("name,codec", [("zsyn_lz4_64k", 1), ("zsyn_lz4_64k", 102), ("zsyn_lz4_256k_linked", 102), ("mix_lz4", 1),
+                                        ("zsyn_zstd3_128k", None), ("zsyn_zstd19_256k", None), ("mix_zstd3", None)])
+def test_emulated_decode_stops_at_job_limits(emu, golden, name, codec):
+    """Batches of small reads decode a frame only up to the last byte they need (zsk_decode_args.limits): the prefix
+    must be exact, the status OK, and nothing may be written outside the frame."""
+    cases, _ = golden
+    c = cases[name]
+    with OraclePort(c["image"]) as op:
+        good = op.decode_all()
+        sizes = np.diff(op.d_off.astype(np.int64))
+        rng = np.random.Generator(np.random.PCG64(9))
+        limits = np.array([int(rng.integers(1, max(2, s + 1))) for s in sizes], dtype=np.uint32)
+        limits[::5] = 1
+        limits[1::7] = sizes[1::7]          # exactly the frame size
+        limits[2::9] = 0xFFFFFFFF           # no limit
+        out, status = emu_api.decode_all(emu, c["image"], codec or op.codec, op.c_off, op.d_off, ctas=2, limits=limits)
+        assert (status == 0).all(), status
+        for f, s in enumerate(sizes):
+            d0, k = int(op.d_off[f]), int(min(int(limits[f]), s))
+            assert (out[d0:d0 + k] == good[d0:d0 + k]).all(), f

@@ -350,3 +350,34 @@ def test_ordered_job_lists(lib, codec, level, frame, monkeypatch, torch_cuda):
             assert rd.decode_frames(lo, hi, dev) == o1 - o0
             got = dev.cpu().numpy()
             assert got[:o1 - o0].tobytes() == data[o0:o1] and (got[o1 - o0:] == 0xEE).all()
+
+
+@pytest.mark.skipif(not have_reference(), reason="oracle/_ref/libzseek_ref.so missing")
+@pytest.mark.parametrize("codec,level,frame", [(LZ4, 0, 65536), (ZSTD, 3, 262144), (ZSTD, 19, 1 << 20)])
+def test_batches_over_partially_decoded_frames(lib, codec, level, frame, torch_cuda):
+    """A batch decodes a missing frame only up to the last byte it needs; the HBM cache then holds a
+    prefix.  Later batches and plain preads that need more of the same frame must still return the reference's bytes."""
+    torch = torch_cuda
+    from datagen import refwriter, zsyn
+    data = zsyn.gen(6 << 20, seed=31)
+    image = refwriter.write(data, codec, level, frame)
+    total = len(data)
+    rng = np.random.Generator(np.random.PCG64(8))
+    with lib.Reader(image=image, cache_size=64) as rd, RefReader(image) as rr:
+        nfr = rd.frames
+        out = torch.zeros(4000 * 4096, dtype=torch.uint8, device="cuda")
+        for rnd, hi_frac in enumerate((0.05, 0.3, 0.1, 1.0, 0.6)):     # how deep into the frames this round reads
+            n = 1500
+            fr = rng.integers(0, nfr, n)
+            inf = (rng.random(n) * hi_frac * frame).astype(np.uint64)
+            offs = np.minimum(rd.d_off[fr].astype(np.uint64) + inf, np.uint64(total - 1))
+            cnt = 4096 if rnd % 2 == 0 else 700
+            out.zero_()
+            res = rd.pread_batch(offs, fixed_count=cnt, dst=out, dst_stride=4096)
+            o = out.cpu().numpy()
+            for i in range(n):
+                r, b = rr.pread(cnt, int(offs[i]))
+                assert res[i] == r and o[i * 4096:i * 4096 + r].tobytes() == b, (rnd, i, int(offs[i]))
+            for _ in range(10):                                        # plain preads see whole frames only
+                off = int(rng.integers(0, total))
+                assert rd.pread(100000, off) == rr.pread(100000, off)
