@@ -381,3 +381,61 @@ def test_batches_over_partially_decoded_frames(lib, codec, level, frame, torch_c
             for _ in range(10):                                        # plain preads see whole frames only
                 off = int(rng.integers(0, total))
                 assert rd.pread(100000, off) == rr.pread(100000, off)
+
+
+@pytest.mark.parametrize("name", ["mix_lz4", "zsyn_zstd3_128k"])
+def test_eight_concurrent_callers_on_one_reader(lib, golden, name, torch_cuda):
+    """zseek_pread and zseek_reader_stats may be called concurrently on one reader.  Eight threads
+    (ctypes releases the GIL inside the calls) mix sequential scans, random reads and stats on ONE reader, four more use
+    readers of their own on the same GPU; every result must be the reference's."""
+    import threading
+    cases, _ = golden
+    c = cases[name]
+    with OraclePort(c["image"]) as op:
+        want = op.decode_all().tobytes()
+        frame_ends = [int(x) for x in op.d_off[1:]]
+    total = len(want)
+    errors = []
+
+    def expect(off, cnt):
+        if off >= total:
+            return b""
+        end = min(off + cnt, next(e for e in frame_ends if e > off))   # B1: never crosses a frame boundary
+        return want[off:end]
+
+    def scan(rd, start, step):
+        try:
+            off = start
+            while off < total:
+                r, b = rd.pread(step, off)
+                assert b == expect(off, step), ("scan", off)
+                off += max(r, 1)
+        except Exception as e:  # noqa: BLE001
+            errors.append(e)
+
+    def rand(rd, seed):
+        try:
+            rng = np.random.Generator(np.random.PCG64(seed))
+            for _ in range(150):
+                off, cnt = int(rng.integers(0, total + 50)), int(rng.choice([1, 100, 4096, 70000]))
+                r, b = rd.pread(cnt, off)
+                assert b == expect(off, cnt) and r == len(b), ("rand", off, cnt)
+                if seed % 2:
+                    st = rd.stats()
+                    assert st.decompressed_size == total
+        except Exception as e:  # noqa: BLE001
+            errors.append(e)
+
+    with lib.Reader(image=c["image"], cache_size=4) as shared:
+        own = [lib.Reader(image=c["image"], cache_size=0) for _ in range(4)]
+        ts = [threading.Thread(target=scan, args=(shared, 0, 4096)), threading.Thread(target=scan, args=(shared, total // 2, 9000))]
+        ts += [threading.Thread(target=rand, args=(shared, s)) for s in range(6)]
+        ts += [threading.Thread(target=scan, args=(own[i], 0, 4096 * (i + 1))) for i in range(2)]
+        ts += [threading.Thread(target=rand, args=(own[2 + i], 50 + i)) for i in range(2)]
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join()
+        for r in own:
+            r.close()
+    assert not errors, errors[:3]
