@@ -939,14 +939,16 @@ bool zseek_b200_load(zseek_reader_t *r, size_t lo, size_t hi, void *call_data, c
 }
 
 /* whole frames [lo, hi) -> device memory, frame f at dst + d_off[f] - d_off[lo]; asynchronous part */
-/* h_job_ids[0 .. hi-lo) = frames [lo, hi) ordered by compressed size, largest first (counting sort over 512-byte
+/* h_job_ids[0 .. hi-lo) = frames [lo, hi) ordered by compressed size, largest first (counting sort over up to 4096
  * size classes; stable, so equal classes stay in file order) */
 static void order_jobs_by_size(zseek_reader_t *r, uint64_t lo, uint64_t hi)
 {
     enum { CLASSES = 4096 };
     static _Thread_local uint32_t start[CLASSES + 1];
     memset(start, 0, sizeof(start));
-#define SIZE_CLASS(f) ((uint32_t)MIN((uint64_t)(CLASSES - 1), (r->c_off[(f) + 1] - r->c_off[(f)]) >> 9))
+    unsigned shift = 0; /* the finest power-of-two class width that still maps the largest frame below CLASSES */
+    while (((uint64_t)r->max_csize >> shift) >= CLASSES) shift++;
+#define SIZE_CLASS(f) ((uint32_t)MIN((uint64_t)(CLASSES - 1), (r->c_off[(f) + 1] - r->c_off[(f)]) >> shift))
     for (uint64_t f = lo; f < hi; f++) start[CLASSES - 1 - SIZE_CLASS(f) + 1]++;
     for (uint32_t c = 0; c < CLASSES; c++) start[c + 1] += start[c];
     for (uint64_t f = lo; f < hi; f++) r->h_job_ids[start[CLASSES - 1 - SIZE_CLASS(f)]++] = (uint32_t)f;

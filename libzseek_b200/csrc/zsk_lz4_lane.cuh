@@ -253,52 +253,43 @@ __global__ void __launch_bounds__(ZSK_LZ4L_THREADS) zsk_lz4_decode_lane_kernel(z
                     ip += 1u;
                     phase = ZSK_L_LLEXT;
                 }
-            } else if (phase == ZSK_L_MATCH) {
-                mlen = min(mrem, min(16u, moffe));
-                muse = moffe;
-                mrem -= mlen;
-                if (mlen == moffe) moffe *= 2u; /* a full period was appended: the pattern now repeats with twice the period */
-                if (mrem == 0u) phase = ZSK_L_TOKEN;
-            } else if (phase == ZSK_L_LIT) {
-                nlit = min(lrem, 8u);
-                if (nlit > bend - ip) {
+            } else if (phase != ZSK_L_BLOCK) {
+                /* continuation phases (rest of a match, rest of a literal run, offset after a long literal run, length
+                 * extension bytes): one block of select logic, so that lanes in different continuation phases share
+                 * one pass of the warp instead of one pass per phase */
+                const bool is_m = phase == ZSK_L_MATCH, is_l = phase == ZSK_L_LIT, is_o = phase == ZSK_L_OFF;
+                const uint32_t ln = min(lrem, 8u), mn = min(mrem, min(16u, moffe));
+                const uint32_t eat = is_m ? 0u : (is_l ? ln : (is_o ? 2u : 1u));
+                if (eat > bend - ip) {
                     st = ZSK_ST_TRUNC;
                 } else {
-                    ip += nlit;
-                    lrem -= nlit;
-                    if (lrem == 0u) phase = (ip == bend) ? ZSK_L_BLOCK : ZSK_L_OFF;
-                }
-            } else if (phase == ZSK_L_LLEXT || phase == ZSK_L_MLEXT) {
-                if (ip >= bend) st = ZSK_ST_TRUNC;
-                else {
-                    const uint32_t b = a0 & 0xffu;
-                    ip += 1u;
-                    if (phase == ZSK_L_LLEXT) {
-                        lrem += b;
-                        if (b != 255u) phase = ZSK_L_LIT;
-                    } else {
-                        mrem += b;
-                        if (b != 255u) {
-                            moffe = moff;
-                            phase = ZSK_L_MATCH;
-                        }
-                    }
-                }
-            } else if (phase == ZSK_L_OFF) {
-                if (bend - ip < 2u) st = ZSK_ST_TRUNC;
-                else {
-                    const uint32_t off = a0 & 0xffffu;
-                    ip += 2u;
-                    if (off == 0u || off > opp) st = ZSK_ST_OFFSET;
-                    else {
+                    ip += eat;
+                    if (is_m) {
+                        mlen = mn;
+                        muse = moffe;
+                        mrem -= mn;
+                        if (mn == moffe) moffe *= 2u; /* a full period was appended: the pattern now repeats with twice the period */
+                        if (mrem == 0u) phase = ZSK_L_TOKEN;
+                    } else if (is_l) {
+                        nlit = ln;
+                        lrem -= ln;
+                        if (lrem == 0u) phase = (ip == bend) ? ZSK_L_BLOCK : ZSK_L_OFF;
+                    } else if (is_o) {
+                        const uint32_t off = a0 & 0xffffu;
+                        if (off == 0u || off > opp) st = ZSK_ST_OFFSET;
                         moff = off;
-                        if (mnib == 15u) {
-                            mrem = 19u;
-                            phase = ZSK_L_MLEXT;
+                        moffe = off;
+                        mrem = mnib == 15u ? 19u : mnib + 4u;
+                        phase = mnib == 15u ? ZSK_L_MLEXT : ZSK_L_MATCH;
+                    } else {
+                        const uint32_t b = a0 & 0xffu;
+                        if (phase == ZSK_L_LLEXT) {
+                            lrem += b;
+                            if (b != 255u) phase = ZSK_L_LIT;
                         } else {
-                            mrem = mnib + 4u;
-                            moffe = off;
-                            phase = ZSK_L_MATCH;
+                            mrem += b;
+                            moffe = moff;
+                            if (b != 255u) phase = ZSK_L_MATCH;
                         }
                     }
                 }
