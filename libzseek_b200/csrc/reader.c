@@ -154,6 +154,7 @@ static const char *status_name(int st)
     case ZSK_ST_TABLE: return "corrupted entropy table";
     case ZSK_ST_UNSUPPORTED: return "dictionary not supported";
     case ZSK_ST_SIZE: return "frame smaller than seek table entry";
+    case ZSK_ST_CHECKSUM: return "checksum mismatch";
     default: return "unknown error";
     }
 }

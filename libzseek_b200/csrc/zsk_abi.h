@@ -26,6 +26,7 @@ enum zsk_status {
     ZSK_ST_TABLE = 7,       /* bad FSE / Huffman description */
     ZSK_ST_UNSUPPORTED = 8, /* dictionary id */
     ZSK_ST_SIZE = 9,        /* frame decodes to fewer bytes than the seek table's dSize */
+    ZSK_ST_CHECKSUM = 10,   /* header / block / content checksum of the frame does not match */
     ZSK_ST_STOPPED = 100    /* kernel-internal: the job's limit was reached (reported as ZSK_ST_OK) */
 };
 

@@ -135,3 +135,111 @@ static __device__ __forceinline__ void zsk_warp_match(uint8_t *out, uint32_t op,
 {
     zsk_group_match<32>(out, op, off, ml, lane, ZSK_FULL);
 }
+
+/* ------------------------------------------------------------------------------------------
+ * XXH32 / XXH64 (the checksums of the LZ4 frame format and of zstd frames; public xxHash
+ * specification).  liblz4 verifies the frame-header, block and content checksums and libzstd the
+ * content checksum whenever a frame carries them, so the reference's zseek_pread fails on a
+ * mismatch (probe: "ERROR_headerChecksum_invalid", "ERROR_blockChecksum_invalid",
+ * "ERROR_contentChecksum_invalid", "Restored data doesn't match checksum"); the kernels do the same.
+ * The four accumulators of a hash are independent chains: the group versions give each of four
+ * lanes one accumulator (one coalesced 16- or 32-byte stripe per step), the serial versions run on
+ * a single lane.  p may have any alignment.
+ * ------------------------------------------------------------------------------------------ */
+#define ZSK_X32_P1 2654435761u
+#define ZSK_X32_P2 2246822519u
+#define ZSK_X32_P3 3266489917u
+#define ZSK_X32_P4 668265263u
+#define ZSK_X32_P5 374761393u
+#define ZSK_X64_P1 11400714785074694791ull
+#define ZSK_X64_P2 14029467366897019727ull
+#define ZSK_X64_P3 1609587929392839161ull
+#define ZSK_X64_P4 9650029242287828579ull
+#define ZSK_X64_P5 2870177450012600261ull
+
+static __device__ __forceinline__ uint32_t zsk_rotl32(uint32_t x, unsigned r) { return (x << r) | (x >> (32 - r)); }
+static __device__ __forceinline__ uint64_t zsk_rotl64(uint64_t x, unsigned r) { return (x << r) | (x >> (64 - r)); }
+static __device__ __forceinline__ uint32_t zsk_x32_round(uint32_t acc, uint32_t w) { return zsk_rotl32(acc + w * ZSK_X32_P2, 13) * ZSK_X32_P1; }
+static __device__ __forceinline__ uint64_t zsk_x64_round(uint64_t acc, uint64_t w) { return zsk_rotl64(acc + w * ZSK_X64_P2, 31) * ZSK_X64_P1; }
+static __device__ __forceinline__ uint32_t zsk_ldb32(const uint8_t *p) /* plain (coherent) loads: p may be data this kernel wrote */
+{
+    return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
+}
+
+/* tail of XXH32 after the stripes: h already holds the merged accumulators (or seed + P5) */
+static __device__ __forceinline__ uint32_t zsk_xxh32_finish(uint32_t h, const uint8_t *p, uint32_t rest, uint32_t len)
+{
+    h += len;
+    while (rest >= 4) { h = zsk_rotl32(h + zsk_ldb32(p) * ZSK_X32_P3, 17) * ZSK_X32_P4; p += 4; rest -= 4; }
+    while (rest) { h = zsk_rotl32(h + (uint32_t)(*p) * ZSK_X32_P5, 11) * ZSK_X32_P1; p++; rest--; }
+    h ^= h >> 15; h *= ZSK_X32_P2; h ^= h >> 13; h *= ZSK_X32_P3; h ^= h >> 16;
+    return h;
+}
+
+static __device__ uint32_t zsk_xxh32_serial(const uint8_t *p, uint32_t len)
+{
+    uint32_t h, done = 0;
+    if (len >= 16) {
+        uint32_t v1 = ZSK_X32_P1 + ZSK_X32_P2, v2 = ZSK_X32_P2, v3 = 0, v4 = 0u - ZSK_X32_P1;
+        for (; done + 16 <= len; done += 16) {
+            v1 = zsk_x32_round(v1, zsk_ldb32(p + done));
+            v2 = zsk_x32_round(v2, zsk_ldb32(p + done + 4));
+            v3 = zsk_x32_round(v3, zsk_ldb32(p + done + 8));
+            v4 = zsk_x32_round(v4, zsk_ldb32(p + done + 12));
+        }
+        h = zsk_rotl32(v1, 1) + zsk_rotl32(v2, 7) + zsk_rotl32(v3, 12) + zsk_rotl32(v4, 18);
+    } else {
+        h = ZSK_X32_P5;
+    }
+    return zsk_xxh32_finish(h, p + done, len - done, len);
+}
+
+/* XXH32 by four consecutive lanes (gl = 0..3 inside the group, gmask = their lane mask); every lane gets the hash */
+static __device__ uint32_t zsk_xxh32_group4(const uint8_t *p, uint32_t len, unsigned gl, unsigned gmask)
+{
+    uint32_t h, done = 0;
+    if (len >= 16) {
+        uint32_t v = gl == 0 ? ZSK_X32_P1 + ZSK_X32_P2 : gl == 1 ? ZSK_X32_P2 : gl == 2 ? 0u : 0u - ZSK_X32_P1;
+        for (; done + 16 <= len; done += 16) v = zsk_x32_round(v, zsk_ldb32(p + done + 4 * gl));
+        const uint32_t r = zsk_rotl32(v, gl == 0 ? 1 : gl == 1 ? 7 : gl == 2 ? 12 : 18);
+        h = r + __shfl_xor_sync(gmask, r, 1);
+        h += __shfl_xor_sync(gmask, h, 2);
+    } else {
+        h = ZSK_X32_P5;
+    }
+    return zsk_xxh32_finish(h, p + done, len - done, len);
+}
+
+/* XXH64 by four consecutive lanes; every lane gets the hash */
+static __device__ uint64_t zsk_xxh64_group4(const uint8_t *p, uint64_t len, unsigned gl, unsigned gmask)
+{
+    uint64_t h, done = 0;
+    if (len >= 32) {
+        uint64_t v = gl == 0 ? ZSK_X64_P1 + ZSK_X64_P2 : gl == 1 ? ZSK_X64_P2 : gl == 2 ? 0ull : 0ull - ZSK_X64_P1;
+        for (; done + 32 <= len; done += 32) {
+            const uint8_t *q = p + done + 8 * gl;
+            v = zsk_x64_round(v, (uint64_t)zsk_ldb32(q) | ((uint64_t)zsk_ldb32(q + 4) << 32));
+        }
+        const uint64_t v1 = __shfl_sync(gmask, v, 0, 4), v2 = __shfl_sync(gmask, v, 1, 4), v3 = __shfl_sync(gmask, v, 2, 4),
+                       v4 = __shfl_sync(gmask, v, 3, 4);
+        h = zsk_rotl64(v1, 1) + zsk_rotl64(v2, 7) + zsk_rotl64(v3, 12) + zsk_rotl64(v4, 18);
+        h = (h ^ zsk_x64_round(0, v1)) * ZSK_X64_P1 + ZSK_X64_P4;
+        h = (h ^ zsk_x64_round(0, v2)) * ZSK_X64_P1 + ZSK_X64_P4;
+        h = (h ^ zsk_x64_round(0, v3)) * ZSK_X64_P1 + ZSK_X64_P4;
+        h = (h ^ zsk_x64_round(0, v4)) * ZSK_X64_P1 + ZSK_X64_P4;
+    } else {
+        h = ZSK_X64_P5;
+    }
+    h += len;
+    const uint8_t *q = p + done;
+    uint64_t rest = len - done;
+    while (rest >= 8) {
+        const uint64_t k = zsk_x64_round(0, (uint64_t)zsk_ldb32(q) | ((uint64_t)zsk_ldb32(q + 4) << 32));
+        h = zsk_rotl64(h ^ k, 27) * ZSK_X64_P1 + ZSK_X64_P4;
+        q += 8; rest -= 8;
+    }
+    if (rest >= 4) { h = zsk_rotl64(h ^ ((uint64_t)zsk_ldb32(q) * ZSK_X64_P1), 23) * ZSK_X64_P2 + ZSK_X64_P3; q += 4; rest -= 4; }
+    while (rest) { h = zsk_rotl64(h ^ ((uint64_t)(*q) * ZSK_X64_P5), 11) * ZSK_X64_P1; q++; rest--; }
+    h ^= h >> 33; h *= ZSK_X64_P2; h ^= h >> 29; h *= ZSK_X64_P3; h ^= h >> 32;
+    return h;
+}

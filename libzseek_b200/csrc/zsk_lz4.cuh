@@ -20,6 +20,13 @@
 
 #define ZSK_LZ4_MAGIC 0x184D2204u
 
+/* LZ4 frame header checksum: second byte of XXH32 over the descriptor (FLG, BD, optional content size and dictID),
+ * i.e. bytes [4, hc_pos) of the frame; liblz4 always verifies it ("ERROR_headerChecksum_invalid"). */
+static __device__ __forceinline__ bool zsk_lz4_header_checksum_ok(const uint8_t *src, uint32_t hc_pos)
+{
+    return ((zsk_xxh32_serial(src + 4, hc_pos - 4) >> 8) & 0xffu) == (uint32_t)ZSK_LDG(src + hc_pos);
+}
+
 /* Decodes one LZ4 block of n bytes at src into out[*pop ...); returns a zsk_status.
  *
  * G = 8 lanes work on the block; four such groups (four different frames) share a warp and run the
@@ -143,6 +150,7 @@ static __device__ __forceinline__ int zsk_lz4_frame_group(const uint8_t *__restr
         ip += 4;
     }
     if (n - ip < 1) return ZSK_ST_TRUNC;
+    if (!zsk_lz4_header_checksum_ok(src, ip)) return ZSK_ST_CHECKSUM;
     ip += 1; /* header checksum byte */
     uint32_t op = 0;
     for (;;) {
@@ -383,7 +391,7 @@ __global__ void __launch_bounds__(ZSK_LZ4_CTA_THREADS, ZSK_LZ4_MIN_CTAS) zsk_lz4
                             else { content_size = zsk_rd64(src + ip); ip += 8; }
                         }
                         if (!st && (flg & 1)) { if (n - ip < 4) st = ZSK_ST_TRUNC; else ip += 4; }
-                        if (!st) { if (n - ip < 1) st = ZSK_ST_TRUNC; else ip += 1; }
+                        if (!st) { if (n - ip < 1) st = ZSK_ST_TRUNC; else if (!zsk_lz4_header_checksum_ok(src, ip)) st = ZSK_ST_CHECKSUM; else ip += 1; }
                         if (!st) state = ZSK_LZ4_S_BLOCK;
                     }
                 }
@@ -427,7 +435,7 @@ __global__ void __launch_bounds__(ZSK_LZ4_CTA_THREADS) zsk_lz4_decode_batch_kern
     int state = ZSK_LZ4_W_FETCH;
     const uint8_t *src = nullptr;
     uint8_t *out = nullptr;
-    uint32_t n = 0, ip = 0, bend = 0, op = 0, cap = 0, job = 0, flags = 0, max_block = 0, stop = 0xffffffffu;
+    uint32_t n = 0, ip = 0, bend = 0, op = 0, cap = 0, job = 0, flags = 0, max_block = 0, stop = 0xffffffffu, bstart = 0;
     uint64_t content_size = 0;
     for (;;) {
         __syncwarp(); /* orders the previous trip's stores before this trip's loads */
@@ -583,8 +591,10 @@ __global__ void __launch_bounds__(ZSK_LZ4_CTA_THREADS) zsk_lz4_decode_batch_kern
             }
             if (!st && op >= stop) frame_end = true; /* the caller needs no byte beyond `stop` of this frame */
         } else if (state == ZSK_LZ4_W_BLOCK) {
-            if (bend && (flags & 16)) { /* block checksum after the compressed block just finished */
-                if (n - ip < 4) st = ZSK_ST_TRUNC; else ip += 4;
+            if (bend && (flags & 16)) { /* block checksum after the compressed block just finished: XXH32 of its compressed bytes */
+                if (n - ip < 4) st = ZSK_ST_TRUNC;
+                else if (zsk_xxh32_group4(src + bstart, bend - bstart, lane & 3, ZSK_FULL) != zsk_rd32(src + ip)) st = ZSK_ST_CHECKSUM;
+                else ip += 4;
             }
             bend = 0;
             if (!st && n - ip < 4) st = ZSK_ST_TRUNC;
@@ -595,6 +605,9 @@ __global__ void __launch_bounds__(ZSK_LZ4_CTA_THREADS) zsk_lz4_decode_batch_kern
                     if ((flags & 4) && n - ip < 4) st = ZSK_ST_TRUNC;
                     else if ((flags & 8) && content_size != op) st = ZSK_ST_FORMAT;
                     else if (op != cap) st = ZSK_ST_SIZE;
+                    else if (flags & 4) { /* content checksum: XXH32 of the decoded frame (this warp's stores were ordered by the trip barrier) */
+                        if (zsk_xxh32_group4(out, op, lane & 3, ZSK_FULL) != zsk_rd32(src + ip)) st = ZSK_ST_CHECKSUM;
+                    }
                     frame_end = true;
                 } else {
                     const bool raw = bs >> 31;
@@ -607,12 +620,17 @@ __global__ void __launch_bounds__(ZSK_LZ4_CTA_THREADS) zsk_lz4_decode_batch_kern
                             zsk_group_copy(out + op, src + ip, bs, lane, 32);
                             op += bs;
                             ip += bs;
-                            if (flags & 16) { if (n - ip < 4) st = ZSK_ST_TRUNC; else ip += 4; }
+                            if (flags & 16) {
+                                if (n - ip < 4) st = ZSK_ST_TRUNC;
+                                else if (zsk_xxh32_group4(src + ip - bs, bs, lane & 3, ZSK_FULL) != zsk_rd32(src + ip)) st = ZSK_ST_CHECKSUM;
+                                else ip += 4;
+                            }
                             if (!st && op >= stop) frame_end = true;
                         }
                     } else if (bs == 0) {
                         st = ZSK_ST_FORMAT;
                     } else {
+                        bstart = ip;
                         bend = ip + bs;
                         state = ZSK_LZ4_W_SEQ;
                     }
@@ -646,7 +664,7 @@ __global__ void __launch_bounds__(ZSK_LZ4_CTA_THREADS) zsk_lz4_decode_batch_kern
                         else { content_size = zsk_rd64(src + ip); ip += 8; }
                     }
                     if (!st && (flg & 1)) { if (n - ip < 4) st = ZSK_ST_TRUNC; else ip += 4; }
-                    if (!st) { if (n - ip < 1) st = ZSK_ST_TRUNC; else ip += 1; }
+                    if (!st) { if (n - ip < 1) st = ZSK_ST_TRUNC; else if (!zsk_lz4_header_checksum_ok(src, ip)) st = ZSK_ST_CHECKSUM; else ip += 1; }
                     if (!st) state = ZSK_LZ4_W_BLOCK;
                 }
             }

@@ -74,6 +74,7 @@ enum {
  * [31:16] near: match offset / staged: source misalignment inside its 16-byte chunk / end: status */
 #define ZSK_L_MOP_FAR 0x200u
 #define ZSK_L_MOP_END 0x400u
+#define ZSK_L_MOP_CK 0x800u /* with END: the literal word carries the frame's content checksum, to be verified */
 
 /* ---- cp.async (LDGSTS): 16-byte global -> shared copies that occupy no registers and stall nobody */
 #ifdef ZSK_EMU
@@ -161,7 +162,7 @@ __global__ void __launch_bounds__(ZSK_LZ4L_THREADS) zsk_lz4_decode_lane_kernel(z
     uint32_t n = 0, ip = 0, bend = 0, opp = 0, cap = 0, job = 0, flags = 0, max_block = 0;
     uint32_t sal = 0, oal = 0;    /* misalignment of src inside its 16-byte chunk / of out inside its 32-byte sector */
     uint32_t fx = 0, fhist = 0;   /* input ring refills issued up to fx (ip + sal coordinates); refill flags of the last DEPTH trips */
-    uint32_t lrem = 0, mrem = 0, moff = 0, moffe = 0, mnib = 0, drain = 0, stop = 0xffffffffu;
+    uint32_t lrem = 0, mrem = 0, moff = 0, moffe = 0, mnib = 0, drain = 0, stop = 0xffffffffu, bstart = 0, cksum = 0;
     uint64_t content_size = 0;
     /* executor state */
     uint32_t ope = 0, flushed = 0; /* decoded bytes [0, ope) are in the ring or in global memory, [0, flushed) in global memory */
@@ -175,7 +176,7 @@ __global__ void __launch_bounds__(ZSK_LZ4L_THREADS) zsk_lz4_decode_lane_kernel(z
         if (__all_sync(ZSK_FULL, phase == ZSK_L_DONE)) break;
         const bool streaming = phase >= ZSK_L_BLOCK && phase <= ZSK_L_MATCH;
         int st = ZSK_ST_OK;
-        bool frame_end = false;
+        bool frame_end = false, verify = false;
 
         /* ---- 1. input ring refill (lands within DEPTH trips) */
         const uint32_t x = ip + sal, xend = sal + n;
@@ -295,15 +296,20 @@ __global__ void __launch_bounds__(ZSK_LZ4L_THREADS) zsk_lz4_decode_lane_kernel(z
                 }
             } else { /* ZSK_L_BLOCK */
                 const uint32_t skip = (bend && (flags & 16u)) ? 4u : 0u; /* block checksum after the block just finished */
-                bend = 0;
                 if (n - ip < skip + 4u) st = ZSK_ST_TRUNC;
-                else {
+                else if (skip && zsk_xxh32_serial(src + bstart, bend - bstart) != a0) st = ZSK_ST_CHECKSUM; /* XXH32 of its compressed bytes */
+                bend = 0;
+                if (!st) {
                     uint32_t bs = skip ? a1 : a0;
                     ip += skip + 4u;
                     if (bs == 0u) { /* EndMark */
                         if ((flags & 4u) && n - ip < 4u) st = ZSK_ST_TRUNC;
                         else if ((flags & 8u) && content_size != opp) st = ZSK_ST_FORMAT;
                         else if (opp != cap) st = ZSK_ST_SIZE;
+                        else if (flags & 4u) { /* content checksum: the executor verifies it once the frame is written */
+                            cksum = skip ? a2 : a1;
+                            verify = true;
+                        }
                         frame_end = true;
                     } else {
                         const bool raw = bs >> 31;
@@ -311,11 +317,13 @@ __global__ void __launch_bounds__(ZSK_LZ4L_THREADS) zsk_lz4_decode_lane_kernel(z
                         if (bs > max_block) st = ZSK_ST_FORMAT;
                         else if (bs > n - ip) st = ZSK_ST_TRUNC;
                         else if (raw) {
+                            bstart = ip;
                             bend = ip + bs;
                             lrem = bs;
                             phase = bs ? ZSK_L_LIT : ZSK_L_BLOCK;
                             if (bs > cap - opp) st = ZSK_ST_DST;
                         } else {
+                            bstart = ip;
                             bend = ip + bs;
                             phase = ZSK_L_TOKEN;
                         }
@@ -328,8 +336,9 @@ __global__ void __launch_bounds__(ZSK_LZ4L_THREADS) zsk_lz4_decode_lane_kernel(z
         /* ---- 4. the new micro-op; a match source older than the ring is copied into this trip's staging slot */
         uint32_t nm, nl0, nl1;
         if (st || frame_end) {
-            nm = ZSK_L_MOP_END | ((uint32_t)st << 16);
-            nl0 = nl1 = 0u;
+            nm = ZSK_L_MOP_END | ((verify && !st) ? ZSK_L_MOP_CK : 0u) | ((uint32_t)st << 16);
+            nl0 = cksum;
+            nl1 = 0u;
             phase = ZSK_L_DRAIN;
             drain = ZSK_LZ4L_DEPTH;
         } else {
@@ -402,13 +411,15 @@ __global__ void __launch_bounds__(ZSK_LZ4L_THREADS) zsk_lz4_decode_lane_kernel(z
                 }
             }
             if (m & ZSK_L_MOP_END) {
+                uint32_t fst = arg;
                 if (arg == 0u) {
                     for (uint32_t i = flushed; i < ope; i++) {
                         const uint32_t y = i + oal;
                         out[i] = (uint8_t)(ZSK_L_OW(y >> 2) >> ((y & 3u) * 8u));
                     }
+                    if ((m & ZSK_L_MOP_CK) && zsk_xxh32_serial(out, ope) != ql0[ZSK_LZ4L_DEPTH - 1]) fst = ZSK_ST_CHECKSUM;
                 }
-                a.status[job] = (int32_t)arg;
+                a.status[job] = (int32_t)fst;
                 ope = 0;
                 flushed = 0;
             }
@@ -458,7 +469,7 @@ __global__ void __launch_bounds__(ZSK_LZ4L_THREADS) zsk_lz4_decode_lane_kernel(z
                             else { content_size = zsk_rd64(src + ip); ip += 8; }
                         }
                         if (!hs && (flg & 1)) { if (n - ip < 4) hs = ZSK_ST_TRUNC; else ip += 4; }
-                        if (!hs) { if (n - ip < 1) hs = ZSK_ST_TRUNC; else ip += 1; }
+                        if (!hs) { if (n - ip < 1) hs = ZSK_ST_TRUNC; else if (!zsk_lz4_header_checksum_ok(src, ip)) hs = ZSK_ST_CHECKSUM; else ip += 1; }
                     }
                 }
                 if (hs) {

@@ -707,6 +707,11 @@ static __device__ int zsk_zstd_frame(zsk_zstd_smem &S, const uint8_t *__restrict
     if (cksum && n - ip < 4) return ZSK_ST_TRUNC;
     if (fcs_sz && fcs != op) return ZSK_ST_FORMAT;
     *produced = op;
+    if (cksum) { /* content checksum: low 32 bits of XXH64 over the decoded frame (the last block ended with a CTA barrier) */
+        int st = ZSK_ST_OK;
+        if (tid < 4 && (uint32_t)zsk_xxh64_group4(out, op, tid, 0xFu) != zsk_rd32(src + ip)) st = ZSK_ST_CHECKSUM;
+        return zsk_cta_status(S, st);
+    }
     return ZSK_ST_OK;
 }
 

@@ -175,3 +175,47 @@ def test_emulated_decode_stops_at_job_limits(emu, golden, name, codec):
         for f, s in enumerate(sizes):
             d0, k = int(op.d_off[f]), int(min(int(limits[f]), s))
             assert (out[d0:d0 + k] == good[d0:d0 + k]).all(), f
+
+
+def _checksum_cases():
+    from datagen import foreign, zsyn
+    rng = np.random.Generator(np.random.PCG64(21))
+    data = zsyn.gen(260000, seed=3) + bytes(5000) + rng.integers(0, 256, 70000, dtype=np.uint8).tobytes() + b"xyz"
+    yield "lz4", data, foreign.build(data, 100000, "lz4", block_checksum=True, content_checksum=True)
+    yield "lz4_no_content_size", data, foreign.build(data, 100000, "lz4", block_checksum=True, content_checksum=True, content_size=False)
+    yield "zstd", data, foreign.build(data, 100000, "zstd", checksum=True)
+
+
+def test_emulated_kernels_verify_checksums_like_the_reference(emu):
+    """liblz4 verifies header, block and content checksums and libzstd the content checksum, so the reference's cached
+    zseek_pread fails on a mismatch; the kernels must accept the intact files and reject exactly the frames the
+    reference rejects (probe and expectations come from the reference itself)."""
+    from oracle.pyapi import RefReader, have_reference
+    if not have_reference():
+        pytest.skip("needs oracle/_ref (the reference build) for the expected verdicts")
+    for name, data, good in _checksum_cases():
+        with OraclePort(good) as op:
+            c_off, d_off, codec = op.c_off.copy(), op.d_off.copy(), op.codec
+        kernels = (1, 102) if name.startswith("lz4") else (codec,)
+        c0, c1, c2 = int(c_off[0]), int(c_off[1]), int(c_off[2])
+        flips = {"intact": None, "content checksum of frame 0": c1 - 1, "payload of frame 1": c1 + (c2 - c1) // 2,
+                 "frame header of frame 1": c1 + 5}
+        for what, pos in flips.items():
+            img = bytearray(good)
+            if pos is not None:
+                img[pos] ^= 0x04
+            want_fail = []
+            for f in range(len(c_off) - 1):
+                # a fresh reader per frame: after a failed frame the reference's LZ4F context stays poisoned and every later
+                # frame fails too (it is not reset on the cached path); the cached path decodes whole frames, like the kernels
+                with RefReader(bytes(img), cache_size=2) as rr:
+                    try:
+                        rr.pread(10, int(d_off[f]))
+                        want_fail.append(False)
+                    except OSError:
+                        want_fail.append(True)
+            for k in kernels:
+                out, status = emu_api.decode_all(emu, bytes(img), k, c_off, d_off, ctas=1)
+                assert [bool(s) for s in status] == want_fail, (name, what, k, status)
+                if pos is None:
+                    assert out.tobytes() == data

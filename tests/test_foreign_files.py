@@ -55,3 +55,33 @@ def test_cuda_path_on_foreign_files(lib, name):
         for _ in range(60):
             off, cnt = int(rng.integers(0, len(data) + 10)), int(rng.choice([1, 4096, 1 << 20]))
             assert rd.pread(cnt, off) == op.pread(cnt, off)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("codec,kw", [("lz4", dict(block_checksum=True, content_checksum=True)), ("zstd", dict(checksum=True))])
+@pytest.mark.parametrize("lane_kernel", [False, True])
+def test_cuda_path_rejects_checksum_mismatches(lib, codec, kw, lane_kernel, monkeypatch):
+    """The reference (through liblz4 / libzstd) fails a zseek_pread whose frame has a wrong header, block or content
+    checksum; so does the CUDA path, frame by frame, while the other frames stay readable."""
+    from datagen import foreign, zsyn
+    if lane_kernel:
+        if codec != "lz4":
+            pytest.skip("LZ4 only")
+        monkeypatch.setenv("ZSEEK_B200_LZ4_LANE_MIN", "0")
+    data = zsyn.gen(400000, seed=13)
+    good = foreign.build(data, 100000, codec, **kw)
+    with OraclePort(good) as op:
+        c_off, d_off = [int(x) for x in op.c_off], [int(x) for x in op.d_off]
+    for what, pos in (("content checksum", c_off[2] - 1), ("payload", c_off[1] + (c_off[2] - c_off[1]) // 2)):
+        img = bytearray(good)
+        img[pos] ^= 0x10                                   # inside frame 1
+        with lib.Reader(image=bytes(img), cache_size=2) as rd:
+            assert rd.pread(1000, d_off[0] + 5)[1] == data[d_off[0] + 5:d_off[0] + 1005]
+            with pytest.raises(lib.ZseekError) as e:
+                rd.pread(1000, d_off[1] + 5)
+            assert str(e.value).startswith("decompress frame"), (what, str(e.value))
+            assert rd.pread(1000, d_off[2] + 5)[1] == data[d_off[2] + 5:d_off[2] + 1005]
+            if have_reference():
+                with RefReader(bytes(img), cache_size=2) as rr:
+                    with pytest.raises(OSError):
+                        rr.pread(1000, d_off[1] + 5)
