@@ -42,11 +42,56 @@ enum {
     ZO_ERR_OFFSET = -5,     /* match offset reaches before the frame start */
     ZO_ERR_BITSTREAM = -6,  /* backward bitstream not exactly consumed / corrupt */
     ZO_ERR_TABLE = -7,      /* bad FSE / Huffman description */
-    ZO_ERR_UNSUPPORTED = -8 /* dictionary id etc. */
+    ZO_ERR_UNSUPPORTED = -8, /* dictionary id etc. */
+    ZO_ERR_CHECKSUM = -9    /* header / block / content checksum mismatch (liblz4 and libzstd verify them, so the reference fails) */
 };
 
 static uint32_t rd_le32(const uint8_t *p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24); }
 static uint64_t rd_le64(const uint8_t *p) { return (uint64_t)rd_le32(p) | ((uint64_t)rd_le32(p + 4) << 32); }
+
+/* XXH32 / XXH64, seed 0 (public xxHash specification): the checksums of the LZ4 frame format (header, block, content)
+ * and of zstd frames (content: low 32 bits of XXH64).  liblz4 / libzstd verify them inside LZ4F_decompress /
+ * ZSTD_decompressDCtx (call sites reference src/decompress.c:537,762), so a mismatch fails the reference's zseek_pread. */
+static uint32_t rotl32(uint32_t x, int r) { return (x << r) | (x >> (32 - r)); }
+static uint64_t rotl64(uint64_t x, int r) { return (x << r) | (x >> (64 - r)); }
+static uint32_t xxh32(const uint8_t *p, size_t len)
+{
+    const uint32_t P1 = 2654435761u, P2 = 2246822519u, P3 = 3266489917u, P4 = 668265263u, P5 = 374761393u;
+    const uint8_t *end = p + len;
+    uint32_t h;
+    if (len >= 16) {
+        uint32_t v[4] = { P1 + P2, P2, 0, 0u - P1 };
+        for (; p + 16 <= end; p += 16)
+            for (int k = 0; k < 4; k++) v[k] = rotl32(v[k] + rd_le32(p + 4 * k) * P2, 13) * P1;
+        h = rotl32(v[0], 1) + rotl32(v[1], 7) + rotl32(v[2], 12) + rotl32(v[3], 18);
+    } else h = P5;
+    h += (uint32_t)len;
+    for (; p + 4 <= end; p += 4) h = rotl32(h + rd_le32(p) * P3, 17) * P4;
+    for (; p < end; p++) h = rotl32(h + *p * P5, 11) * P1;
+    h ^= h >> 15; h *= P2; h ^= h >> 13; h *= P3; h ^= h >> 16;
+    return h;
+}
+static uint64_t xxh64_round(uint64_t acc, uint64_t w) { return rotl64(acc + w * 14029467366897019727ull, 31) * 11400714785074694791ull; }
+static uint64_t xxh64(const uint8_t *p, size_t len)
+{
+    const uint64_t P1 = 11400714785074694791ull, P2 = 14029467366897019727ull, P3 = 1609587929392839161ull,
+                   P4 = 9650029242287828579ull, P5 = 2870177450012600261ull;
+    const uint8_t *end = p + len;
+    uint64_t h;
+    if (len >= 32) {
+        uint64_t v[4] = { P1 + P2, P2, 0, 0ull - P1 };
+        for (; p + 32 <= end; p += 32)
+            for (int k = 0; k < 4; k++) v[k] = xxh64_round(v[k], rd_le64(p + 8 * k));
+        h = rotl64(v[0], 1) + rotl64(v[1], 7) + rotl64(v[2], 12) + rotl64(v[3], 18);
+        for (int k = 0; k < 4; k++) h = (h ^ xxh64_round(0, v[k])) * P1 + P4;
+    } else h = P5;
+    h += (uint64_t)len;
+    for (; p + 8 <= end; p += 8) h = rotl64(h ^ xxh64_round(0, rd_le64(p)), 27) * P1 + P4;
+    if (p + 4 <= end) { h = rotl64(h ^ ((uint64_t)rd_le32(p) * P1), 23) * P2 + P3; p += 4; }
+    for (; p < end; p++) h = rotl64(h ^ (*p * P5), 11) * P1;
+    h ^= h >> 33; h *= P2; h ^= h >> 29; h *= P3; h ^= h >> 32;
+    return h;
+}
 
 /* =====================================================================================
  * Seek table — reference src/seek_table.c:112-176 (read_seek_table), :62-110 (read_st_entries)
@@ -172,7 +217,8 @@ EXPORT ssize_t zo_lz4_frame_decode(const uint8_t *src, size_t n, uint8_t *dst, s
     if (has_csize) { if (ip + 8 > n) return ZO_ERR_TRUNC; content_size = rd_le64(src + ip); ip += 8; }
     if (dict) { if (ip + 4 > n) return ZO_ERR_TRUNC; ip += 4; }
     if (ip + 1 > n) return ZO_ERR_TRUNC;
-    ip += 1;                                              /* header checksum byte (HC) — not verified here */
+    if (((xxh32(src + 4, ip - 4) >> 8) & 0xff) != src[ip]) return ZO_ERR_CHECKSUM; /* HC: second byte of XXH32(descriptor) */
+    ip += 1;
     size_t op = 0;
     for (;;) {
         if (ip + 4 > n) return ZO_ERR_TRUNC;
@@ -192,10 +238,18 @@ EXPORT ssize_t zo_lz4_frame_decode(const uint8_t *src, size_t n, uint8_t *dst, s
             if (r) return r;
         }
         ip += bs;
-        if (block_cksum) { if (ip + 4 > n) return ZO_ERR_TRUNC; ip += 4; }
+        if (block_cksum) {                                   /* XXH32 of the block's compressed bytes */
+            if (ip + 4 > n) return ZO_ERR_TRUNC;
+            if (xxh32(src + ip - bs, bs) != rd_le32(src + ip)) return ZO_ERR_CHECKSUM;
+            ip += 4;
+        }
     }
-    if (content_cksum) { if (ip + 4 > n) return ZO_ERR_TRUNC; ip += 4; }
     if (has_csize && content_size != op) return ZO_ERR_FORMAT;
+    if (content_cksum) {                                     /* XXH32 of the decoded frame */
+        if (ip + 4 > n) return ZO_ERR_TRUNC;
+        if (xxh32(dst, op) != rd_le32(src + ip)) return ZO_ERR_CHECKSUM;
+        ip += 4;
+    }
     return (ssize_t)op;
 }
 
@@ -640,8 +694,12 @@ EXPORT ssize_t zo_zstd_frame_decode(const uint8_t *src, size_t n, uint8_t *dst, 
     free(st->lit);
     free(st);
     if (r) return r;
-    if (cksum) { if (ip + 4 > n) return ZO_ERR_TRUNC; ip += 4; }
     if (has_fcs && fcs != op) return ZO_ERR_FORMAT;
+    if (cksum) {                                             /* low 32 bits of XXH64 of the decoded frame */
+        if (ip + 4 > n) return ZO_ERR_TRUNC;
+        if ((uint32_t)xxh64(dst, op) != rd_le32(src + ip)) return ZO_ERR_CHECKSUM;
+        ip += 4;
+    }
     return (ssize_t)op;
 }
 

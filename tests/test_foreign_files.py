@@ -85,3 +85,35 @@ def test_cuda_path_rejects_checksum_mismatches(lib, codec, kw, lane_kernel, monk
                 with RefReader(bytes(img), cache_size=2) as rr:
                     with pytest.raises(OSError):
                         rr.pread(1000, d_off[1] + 5)
+
+
+@pytest.mark.skipif(not have_reference(), reason="oracle/_ref not built (needs /root/reference)")
+@pytest.mark.parametrize("codec,kw", [("lz4", dict(block_checksum=True, content_checksum=True)),
+                                      ("lz4", dict(content_checksum=True, content_size=False, block_size_id=5)),
+                                      ("zstd", dict(checksum=True))])
+def test_oracle_port_verifies_checksums_like_the_reference(codec, kw):
+    """Same verdict, frame by frame, as the reference's whole-frame (cached) path on files with one flipped bit in a
+    frame header, in a frame's payload and in a content checksum (a fresh reference reader per frame)."""
+    from datagen import foreign, zsyn
+    data = zsyn.gen(350000, seed=17) + bytes(3000)
+    good = foreign.build(data, 100000, codec, **kw)
+    with OraclePort(good) as op:
+        c_off, d_off = [int(x) for x in op.c_off], [int(x) for x in op.d_off]
+        nfr = op.frames
+    for pos in (None, c_off[0] + 5, c_off[1] + (c_off[2] - c_off[1]) // 2, c_off[3] - 2):
+        img = bytearray(good)
+        if pos is not None:
+            img[pos] ^= 0x20
+        for f in range(nfr):
+            with RefReader(bytes(img), cache_size=1) as rr, OraclePort(bytes(img)) as op:
+                try:
+                    want = rr.pread(50, d_off[f])
+                except OSError:
+                    want = None
+                try:
+                    got = op.decode_frame(f).tobytes()[:50]
+                except OSError:
+                    got = None
+                assert (got is None) == (want is None), (codec, pos, f)
+                if want is not None:
+                    assert got == want[1]
