@@ -128,7 +128,7 @@ static __device__ __forceinline__ void zsk_l_ring_write(uint32_t *outr, uint32_t
     const uint32_t a = y & 3u, s = a * 8u, j = y >> 2, nb = a + len;
     if (len) {
         const uint32_t old = ZSK_L_OW(j);
-        const uint32_t keep = s ? (old & (0xffffffffu >> (32u - s))) : 0u;
+        const uint32_t keep = old & ~(0xffffffffu << s); /* the a bytes below y stay */
         ZSK_L_OW(j) = keep | (x[0] << s);
     }
 #pragma unroll
@@ -394,9 +394,9 @@ __global__ void __launch_bounds__(ZSK_LZ4L_THREADS) zsk_lz4_decode_lane_kernel(z
                 const uint32_t chunk = (flushed == 0u && oal) ? 32u - oal : 32u;
                 if (ope - flushed >= chunk) {
                     if (chunk == 32u) {
-                        const uint32_t j = (flushed + oal) >> 2;
-                        const uint4 v0 = make_uint4(ZSK_L_OW(j), ZSK_L_OW(j + 1), ZSK_L_OW(j + 2), ZSK_L_OW(j + 3));
-                        const uint4 v1 = make_uint4(ZSK_L_OW(j + 4), ZSK_L_OW(j + 5), ZSK_L_OW(j + 6), ZSK_L_OW(j + 7));
+                        const uint32_t *fp = &ZSK_L_OW((flushed + oal) >> 2); /* 32-byte aligned: the 8 words do not wrap */
+                        const uint4 v0 = make_uint4(fp[0], fp[32], fp[64], fp[96]);
+                        const uint4 v1 = make_uint4(fp[128], fp[160], fp[192], fp[224]);
                         uint4 *o = (uint4 *)(out + flushed);
                         o[0] = v0;
                         o[1] = v1;
