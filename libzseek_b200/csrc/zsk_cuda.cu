@@ -12,6 +12,7 @@
 #include "zsk_cuda.h"
 #include "zsk_lz4.cuh"
 #include "zsk_lz4_lane.cuh"
+#include "zsk_lz4_lane2.cuh"
 #include "zsk_zstd.cuh"
 #include "zsk_seek.cuh"
 
@@ -33,6 +34,7 @@ struct zsk_cuda_ctx {
     int zstd_ctas, lz4_ctas;
     int lz4_group;                       /* lanes per LZ4 frame (ZSEEK_B200_LZ4_GROUP: 4, 8, 16 or 32) */
     int lz4_lane_ctas;                   /* resident CTAs of the lane-per-frame kernel */
+    int lz4_lane2, lz4_lane2_ctas;       /* ZSEEK_B200_LZ4_LANE2=1: the two-micro-ops-per-trip variant */
     unsigned lz4_lane_min;               /* launches with at least this many frames use the lane-per-frame kernel */
     unsigned long long launches;
     int trace;                           /* ZSEEK_B200_TRACE=1: timeline of the host-destination pipeline */
@@ -137,6 +139,16 @@ int zsk_cuda_ctx_create(int device, zsk_cuda_ctx **out, char *err, size_t errlen
         if (v >= 1 && v < per_sm) per_sm = v;
     }
     cx->lz4_lane_ctas = per_sm * cx->sm_count;
+    CK0(cudaFuncSetAttribute(zsk_lz4_decode_lane2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ZSK_LZ4L2_SMEM));
+    CK0(cudaFuncSetAttribute(zsk_lz4_decode_lane2_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    CK0(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, zsk_lz4_decode_lane2_kernel, ZSK_LZ4L_THREADS, ZSK_LZ4L2_SMEM));
+    if (per_sm < 1) per_sm = 1;
+    if (const char *g = getenv("ZSEEK_B200_LZ4_LANE_CTAS_PER_SM")) {
+        int v = atoi(g);
+        if (v >= 1 && v < per_sm) per_sm = v;
+    }
+    cx->lz4_lane2_ctas = per_sm * cx->sm_count;
+    if (const char *g = getenv("ZSEEK_B200_LZ4_LANE2")) cx->lz4_lane2 = atoi(g);
     cx->lz4_lane_min = 40960;             /* measured crossover: 32,768 frames 11.6 ms (warp per frame) vs 14.1 ms (lane per frame), 49,152 frames 18.6 vs 15.9 ms */
     if (const char *g = getenv("ZSEEK_B200_LZ4_LANE_MIN")) cx->lz4_lane_min = (unsigned)strtoul(g, NULL, 10); /* 0 = always, huge = never */
     CK0(cudaMalloc((void **)&cx->scratch, (size_t)cx->zstd_ctas * ZSK_LIT_SCRATCH + ZSK_PAD_BACK));
@@ -311,9 +323,15 @@ int zsk_cuda_launch_decode(zsk_cuda_ctx *cx, int codec, const zsk_decode_args *a
     CK(cx, cudaEventRecord(cx->k0, s));
     if (codec == ZSK_CODEC_LZ4 && cx->lz4_group == 401 && a.njobs >= cx->lz4_lane_min) {
         unsigned ctas = (a.njobs + ZSK_LZ4L_THREADS - 1) / ZSK_LZ4L_THREADS;
-        if (ctas > (unsigned)cx->lz4_lane_ctas) ctas = (unsigned)cx->lz4_lane_ctas;
-        zsk_lz4_decode_lane_kernel<<<ctas, ZSK_LZ4L_THREADS, ZSK_LZ4L_SMEM, s>>>(a);
-        cx->k_name = "zsk_lz4_decode_lane_kernel";
+        if (cx->lz4_lane2) {
+            if (ctas > (unsigned)cx->lz4_lane2_ctas) ctas = (unsigned)cx->lz4_lane2_ctas;
+            zsk_lz4_decode_lane2_kernel<<<ctas, ZSK_LZ4L_THREADS, ZSK_LZ4L2_SMEM, s>>>(a);
+            cx->k_name = "zsk_lz4_decode_lane2_kernel";
+        } else {
+            if (ctas > (unsigned)cx->lz4_lane_ctas) ctas = (unsigned)cx->lz4_lane_ctas;
+            zsk_lz4_decode_lane_kernel<<<ctas, ZSK_LZ4L_THREADS, ZSK_LZ4L_SMEM, s>>>(a);
+            cx->k_name = "zsk_lz4_decode_lane_kernel";
+        }
     } else if (codec == ZSK_CODEC_LZ4) {
         unsigned frames_per_cta = ZSK_LZ4_CTA_THREADS / (unsigned)(cx->lz4_group > 1 ? cx->lz4_group % 100 : 8);
         if (cx->lz4_group == 401) frames_per_cta = ZSK_LZ4_CTA_THREADS / 32;

@@ -5,6 +5,7 @@
 #include "cuda_emu.h"
 #include "../../libzseek_b200/csrc/zsk_lz4.cuh"
 #include "../../libzseek_b200/csrc/zsk_lz4_lane.cuh"
+#include "../../libzseek_b200/csrc/zsk_lz4_lane2.cuh"
 #include "../../libzseek_b200/csrc/zsk_zstd.cuh"
 #include "../../libzseek_b200/csrc/zsk_seek.cuh"
 
@@ -25,6 +26,7 @@ void emu_decode(int codec, const uint8_t *comp, uint64_t comp_base, const uint64
     a.status = status; a.work_counter = &counter; a.scratch = scratch.data(); a.limits = limits;
     if (codec == 1) emu::launch(dim3(ctas), dim3(ZSK_LZ4_CTA_THREADS), 0, [&] { zsk_lz4_decode_batch_kernel(a); });           /* shipped default */
     else if (codec == 101) emu::launch(dim3(ctas), dim3(ZSK_LZ4_CTA_THREADS), 0, [&] { zsk_lz4_decode_lockstep_kernel<8>(a); }); /* alternative */
+    else if (codec == 103) emu::launch(dim3(ctas), dim3(ZSK_LZ4L_THREADS), ZSK_LZ4L2_SMEM, [&] { zsk_lz4_decode_lane2_kernel(a); }); /* two micro-ops per trip */
     else if (codec == 102) emu::launch(dim3(ctas), dim3(ZSK_LZ4L_THREADS), ZSK_LZ4L_SMEM, [&] { zsk_lz4_decode_lane_kernel(a); });  /* many-frame launches */
     else emu::launch(dim3(ctas), dim3(ZSK_ZSTD_CTA_THREADS), 0, [&] { zsk_zstd_decode_kernel(a); });
 }
