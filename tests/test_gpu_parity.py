@@ -266,6 +266,7 @@ def test_reference_example_binary_runs_against_b200_reader(flag, tmp_path, torch
 LZ4_KERNEL_ENVS = {
     "lane_per_frame": {"ZSEEK_B200_LZ4_LANE_MIN": "0", "ZSEEK_B200_SORT_MIN": "0"},           # the kernel big launches get
     "lane_per_frame_ordered_jobs": {"ZSEEK_B200_LZ4_LANE_MIN": "0", "ZSEEK_B200_SORT_MIN": "1"},
+    "lane_per_frame_two_per_trip": {"ZSEEK_B200_LZ4_LANE_MIN": "0", "ZSEEK_B200_LZ4_LANE2": "1", "ZSEEK_B200_SORT_MIN": "1"},
     "warp_per_frame": {"ZSEEK_B200_LZ4_LANE_MIN": "4000000000"},                              # the kernel small launches get
     "lockstep_groups": {"ZSEEK_B200_LZ4_LANE_MIN": "4000000000", "ZSEEK_B200_LZ4_GROUP": "1"},
 }
@@ -296,8 +297,10 @@ def test_every_lz4_kernel_matches_golden(lib, golden, name, kernel_env, torch_cu
             got = dev.cpu().numpy()
             assert hashlib.sha256(got[lead:lead + total].tobytes()).hexdigest() == c["input_sha256"]
             assert (got[:lead] == 0xEE).all() and (got[lead + total:] == 0xEE).all(), "wrote outside the destination"
-        want_kernel = {"lane": "zsk_lz4_decode_lane_kernel", "warp": "zsk_lz4_decode_batch_kernel", "lock": "zsk_lz4_decode_lockstep_kernel"}
-        key = "lane" if kernel_env.get("ZSEEK_B200_LZ4_LANE_MIN") == "0" else "lock" if "ZSEEK_B200_LZ4_GROUP" in kernel_env else "warp"
+        want_kernel = {"lane": "zsk_lz4_decode_lane_kernel", "lane2": "zsk_lz4_decode_lane2_kernel", "warp": "zsk_lz4_decode_batch_kernel",
+                       "lock": "zsk_lz4_decode_lockstep_kernel"}
+        key = ("lane2" if "ZSEEK_B200_LZ4_LANE2" in kernel_env else "lane" if kernel_env.get("ZSEEK_B200_LZ4_LANE_MIN") == "0"
+               else "lock" if "ZSEEK_B200_LZ4_GROUP" in kernel_env else "warp")
         assert rd.last_decode_kernel == want_kernel[key]
         assert hashlib.sha256(rd.read_range(total + 5, 0)).hexdigest() == c["input_sha256"]
         for off, cnt, ret, digest in c["reads"][:120]:
