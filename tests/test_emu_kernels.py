@@ -186,10 +186,10 @@ def test_emulated_decode_stops_at_job_limits(emu, golden, name, codec):
 def _checksum_cases():
     from datagen import foreign, zsyn
     rng = np.random.Generator(np.random.PCG64(21))
-    data = zsyn.gen(260000, seed=3) + bytes(5000) + rng.integers(0, 256, 70000, dtype=np.uint8).tobytes() + b"xyz"
-    yield "lz4", data, foreign.build(data, 100000, "lz4", block_checksum=True, content_checksum=True)
-    yield "lz4_no_content_size", data, foreign.build(data, 100000, "lz4", block_checksum=True, content_checksum=True, content_size=False)
-    yield "zstd", data, foreign.build(data, 100000, "zstd", checksum=True)
+    data = zsyn.gen(90000, seed=3) + bytes(3000) + rng.integers(0, 256, 30000, dtype=np.uint8).tobytes() + b"xyz"
+    yield "lz4", data, foreign.build(data, 40000, "lz4", block_checksum=True, content_checksum=True)
+    yield "lz4_no_content_size", data, foreign.build(data, 40000, "lz4", block_checksum=True, content_checksum=True, content_size=False)
+    yield "zstd", data, foreign.build(data, 40000, "zstd", checksum=True)
 
 
 def test_emulated_kernels_verify_checksums_like_the_reference(emu):
