@@ -55,6 +55,8 @@ struct zsk_zstd_smem {
     uint32_t job;
 };
 
+static_assert(sizeof(((zsk_zstd_smem *)0)->seq) >= 512 * sizeof(uint32_t), "the sequence ring doubles as the 512-entry FSE table-build scratch: ZSK_SEQ_CHUNK >= 86");
+
 /* CTA-uniform error exchange: every thread passes its own status; if any is non-zero all threads
  * get the same non-zero status back (the barrier also orders shared-memory traffic). */
 static __device__ __forceinline__ int zsk_cta_status(zsk_zstd_smem &S, int st)
