@@ -17,7 +17,7 @@
  *   with 32 lanes; warp-level sync only         writes {LL, ML, offset} to smem
  *   ------------------------------ __syncthreads (per chunk) ------------------
  *
- * All tables live in shared memory (Huffman 4 KiB, FSE 10 KiB, two sequence chunks 2.25 KiB); Huffman
+ * All tables live in shared memory (Huffman 4 KiB, FSE 5 KiB, two sequence chunks 2.25 KiB); Huffman
  * output goes to a per-CTA literal scratch in HBM (L2-resident, <= 128 KiB), the frame's output is
  * written straight to its final place and re-read from L1/L2 for match copies (offsets reach up to
  * the whole frame, far beyond what shared memory could hold for 256 KiB - 1 MiB frames).
@@ -36,9 +36,9 @@
 
 struct zsk_zstd_smem {
     uint16_t huf[2048];                   /* sym | nbBits << 8 */
-    uint2 fse_ll[512];                    /* x = base value of the code, y = next-state base | nbBits << 16 | extra bits << 24 */
-    uint2 fse_ml[512];
-    uint2 fse_of[256];
+    uint32_t fse_ll[512];                 /* [9:0] next-state base, [15:10] nbBits, [22:16] extra bits of the code, [28:23] the code */
+    uint32_t fse_ml[512];
+    uint32_t fse_of[256];
     uint32_t wtab[64];                    /* FSE table of the Huffman weights: sym | nbBits << 8 | base << 16 */
     uint32_t seq[2][ZSK_SEQ_CHUNK][3];    /* literal length, match length, offset; doubles as table-build scratch in stage 1 */
     uint16_t huf_start[256];
@@ -188,20 +188,26 @@ static __device__ const uint8_t ZSK_LL_BITS[36] = { 0,0,0,0,0,0,0,0,0,0,0,0,0,0,
 static __device__ const uint32_t ZSK_ML_BASE[53] = { 3,4,5,6,7,8,9,10,11,12,13,14,15,16,17,18,19,20,21,22,23,24,25,26,27,28,29,30,31,32,33,34,35,37,39,41,43,47,51,59,67,83,99,131,259,515,1027,2051,4099,8195,16387,32771,65539 };
 static __device__ const uint8_t ZSK_ML_BITS[53] = { 0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,1,1,1,1,2,2,3,3,4,4,5,7,8,9,10,11,12,13,14,15,16 };
 
-/* Expands a built table (sym | nb << 8 | base << 16) into decode entries that carry the code's base value and
- * extra-bit count, so the sequence decoder needs one 8-byte shared-memory load per state.  kind: 0 LL, 1 OF, 2 ML.
- * Executed by all 32 lanes of the building warp. */
-static __device__ __forceinline__ void zsk_fse_expand(uint2 *dst, const uint32_t *tmp, int log, int kind, unsigned lane)
+/* Re-packs a built table (sym | nb << 8 | base << 16) into 4-byte decode entries that also carry the code and its
+ * extra-bit count: the state walk needs next-state base, nbBits and the extra-bit count (one 4-byte shared-memory load per
+ * state; the three fields of three entries add up without carries into each other), the extra-bit fetch looks the code's
+ * base value up (zsk_code_base).  kind: 0 LL, 1 OF, 2 ML.  Executed by all 32 lanes of the building warp. */
+static __device__ __forceinline__ void zsk_fse_expand(uint32_t *dst, const uint32_t *tmp, int log, int kind, unsigned lane)
 {
     const uint32_t size = 1u << log;
     for (uint32_t i = lane; i < size; i += 32) {
         const uint32_t e = tmp[i], sym = e & 0xff, nb = (e >> 8) & 0xff, base = e >> 16;
-        uint32_t bv, xb;
-        if (kind == 0) { bv = ZSK_LL_BASE[sym]; xb = ZSK_LL_BITS[sym]; }
-        else if (kind == 2) { bv = ZSK_ML_BASE[sym]; xb = ZSK_ML_BITS[sym]; }
-        else { bv = 1u << sym; xb = sym; }
-        dst[i] = make_uint2(bv, base | (nb << 16) | (xb << 24));
+        const uint32_t xb = kind == 0 ? ZSK_LL_BITS[sym] : kind == 2 ? ZSK_ML_BITS[sym] : sym;
+        dst[i] = (base & 0x3ffu) | (nb << 10) | (xb << 16) | (sym << 23);
     }
+}
+
+static __device__ __forceinline__ uint32_t zsk_entry_nb(uint32_t e) { return (e >> 10) & 0x3fu; }
+static __device__ __forceinline__ uint32_t zsk_entry_xb(uint32_t e) { return (e >> 16) & 0x7fu; }
+static __device__ __forceinline__ uint32_t zsk_code_base(uint32_t e, int kind)
+{
+    const uint32_t sym = e >> 23;
+    return kind == 0 ? ZSK_LL_BASE[sym] : kind == 2 ? ZSK_ML_BASE[sym] : 1u << sym;
 }
 
 /* One of the three sequence tables.  Single thread.  Advances *ip past the description. */
@@ -457,7 +463,7 @@ static __device__ int zsk_zstd_block(zsk_zstd_smem &S, const uint8_t *__restrict
         for (int t = 0; t < 3; t++) {
             const int mode = (modes >> (6 - 2 * t)) & 3;
             int32_t *logp = t == 0 ? &S.log_ll : t == 1 ? &S.log_of : &S.log_ml;
-            uint2 *dst = t == 0 ? S.fse_ll : t == 1 ? S.fse_of : S.fse_ml;
+            uint32_t *dst = t == 0 ? S.fse_ll : t == 1 ? S.fse_of : S.fse_ml;
             if (lane == 0 && !st) {
                 if (t == 0) st = zsk_seq_table(tmp, logp, mode, p, n, &sp, ZSK_LL_DEF, 36, 6, 9, 35, S.probs, S.next);
                 else if (t == 1) st = zsk_seq_table(tmp, logp, mode, p, n, &sp, ZSK_OF_DEF, 29, 5, 8, 31, S.probs, S.next);
@@ -502,21 +508,21 @@ static __device__ int zsk_zstd_block(zsk_zstd_smem &S, const uint8_t *__restrict
                     const uint32_t cnt = min(nseq - first, (uint32_t)ZSK_SEQ_CHUNK);
                     if (lane == 0 && !st) {
                         for (uint32_t i = 0; i < cnt; i++) {
-                            const uint2 el = S.fse_ll[sl], eo = S.fse_of[so], em = S.fse_ml[sm];
+                            const uint32_t el = S.fse_ll[sl], eo = S.fse_of[so], em = S.fse_ml[sm];
                             dstq[i][0] = sl | (so << 10) | (sm << 20);
                             dstq[i][1] = (uint32_t)b.pos;
-                            /* y >> 16 = nbBits | extra bits << 8: the three sums stay inside their bytes (<= 26 and <= 63) */
-                            const uint32_t yl = el.y >> 16, yo = eo.y >> 16, ym = em.y >> 16;
-                            const uint32_t pk = yl + yo + ym;
-                            b.pos -= (int32_t)(pk >> 8);
+                            /* e >> 10 = nbBits (6 bits) | extra bits (7 bits) << 6 | code: the sums of the three nbBits (<= 26) and of
+                             * the three extra-bit counts (<= 63) stay inside their fields */
+                            const uint32_t pk = (el >> 10) + (eo >> 10) + (em >> 10);
+                            b.pos -= (int32_t)((pk >> 6) & 0x7fu);
                             if (first + i + 1 < nseq) {
                                 /* the state bits of LL, ML, OF are adjacent (LL highest): one field of <= 26 bits, then split */
-                                const uint32_t nm = ym & 0xff, no = yo & 0xff, nb = pk & 0xff;
+                                const uint32_t nm = zsk_entry_nb(em), no = zsk_entry_nb(eo), nb = pk & 0x3fu;
                                 zsk_bits_ensure(b, (int32_t)nb);
                                 const uint32_t v = zsk_bits_take(b, nb);
-                                so = (eo.y & 0xffff) + (v & ((1u << no) - 1u));
-                                sm = (em.y & 0xffff) + ((v >> no) & ((1u << nm) - 1u));
-                                sl = (el.y & 0xffff) + (v >> (no + nm));
+                                so = (eo & 0x3ffu) + (v & ((1u << no) - 1u));
+                                sm = (em & 0x3ffu) + ((v >> no) & ((1u << nm) - 1u));
+                                sl = (el & 0x3ffu) + (v >> (no + nm));
                             }
                             if (b.pos < 0) { st = ZSK_ST_BITSTREAM; break; }
                         }
@@ -527,16 +533,16 @@ static __device__ int zsk_zstd_block(zsk_zstd_smem &S, const uint8_t *__restrict
                         const uint8_t *bits_base = p + S.bs_start;
                         for (uint32_t i = lane; i < cnt; i += 32) {
                             const uint32_t ss = dstq[i][0];
-                            const uint2 el = S.fse_ll[ss & 1023u], eo = S.fse_of[(ss >> 10) & 1023u], em = S.fse_ml[ss >> 20];
+                            const uint32_t el = S.fse_ll[ss & 1023u], eo = S.fse_of[(ss >> 10) & 1023u], em = S.fse_ml[ss >> 20];
                             zsk_bits bb;
                             bb.base = bits_base;
                             bb.pos = (int32_t)dstq[i][1];
                             zsk_bits_refill(bb);                       /* >= 57 bits below pos */
-                            const uint32_t xo = eo.y >> 24, xm = em.y >> 24, xl = el.y >> 24;
-                            const uint32_t ov = eo.x + zsk_bits_take(bb, xo);
+                            const uint32_t xo = zsk_entry_xb(eo), xm = zsk_entry_xb(em), xl = zsk_entry_xb(el);
+                            const uint32_t ov = zsk_code_base(eo, 1) + zsk_bits_take(bb, xo);
                             zsk_bits_ensure(bb, (int32_t)(xm + xl));
-                            const uint32_t mlen = em.x + zsk_bits_take(bb, xm);
-                            const uint32_t llen = el.x + zsk_bits_take(bb, xl);
+                            const uint32_t mlen = zsk_code_base(em, 2) + zsk_bits_take(bb, xm);
+                            const uint32_t llen = zsk_code_base(el, 0) + zsk_bits_take(bb, xl);
                             dstq[i][0] = llen; dstq[i][1] = mlen; dstq[i][2] = ov;
                         }
                     }
@@ -717,7 +723,10 @@ static __device__ int zsk_zstd_frame(zsk_zstd_smem &S, const uint8_t *__restrict
     return ZSK_ST_OK;
 }
 
-__global__ void __launch_bounds__(ZSK_ZSTD_CTA_THREADS) zsk_zstd_decode_kernel(zsk_decode_args a)
+#ifndef ZSK_ZSTD_MIN_CTAS
+#define ZSK_ZSTD_MIN_CTAS 16 /* 13.6 KB of shared memory per CTA allow 16 CTAs per SM; this sizes the register allocation for them (64 per thread) */
+#endif
+__global__ void __launch_bounds__(ZSK_ZSTD_CTA_THREADS, ZSK_ZSTD_MIN_CTAS) zsk_zstd_decode_kernel(zsk_decode_args a)
 {
     __shared__ zsk_zstd_smem S;
     uint8_t *lit_scratch = a.scratch + (size_t)blockIdx.x * ZSK_LIT_SCRATCH + 16;
