@@ -225,3 +225,41 @@ def test_emulated_kernels_verify_checksums_like_the_reference(emu):
                 assert [bool(s) for s in status] == want_fail, (name, what, k, status)
                 if pos is None:
                     assert out.tobytes() == data
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_emulated_lz4_kernels_on_random_mixtures(emu, seed):
+    """Property check (decode == the writer's input) on randomly assembled data: runs of random length drawn from text,
+    zeros, noise, short periods and far repeats, compressed by the reference writer at random frame sizes and levels; every
+    shipped LZ4 kernel, aligned and unaligned destinations."""
+    from datagen import refwriter, zsyn
+    from oracle.pyapi import LZ4, have_reference
+    if not have_reference():
+        pytest.skip("inputs come from the reference writer (oracle/_ref)")
+    rng = np.random.Generator(np.random.PCG64(1000 + seed))
+    text = zsyn.gen(200000, seed=seed)
+    parts, total = [], 0
+    while total < 260000:
+        kind, n = int(rng.integers(0, 6)), int(rng.integers(1, 9000))
+        if kind == 0:
+            o = int(rng.integers(0, len(text) - n)); p = text[o:o + n]
+        elif kind == 1:
+            p = bytes(n)
+        elif kind == 2:
+            p = rng.integers(0, 256, n, dtype=np.uint8).tobytes()
+        elif kind == 3:
+            per = rng.integers(0, 256, int(rng.integers(1, 24)), dtype=np.uint8).tobytes(); p = (per * (n // len(per) + 1))[:n]
+        elif kind == 4 and parts:
+            src = b"".join(parts)[-70000:]; o = int(rng.integers(0, max(1, len(src) - 1))); p = src[o:o + n]
+        else:
+            p = rng.integers(97, 101, n, dtype=np.uint8).tobytes()
+        parts.append(p); total += len(p)
+    data = b"".join(parts)
+    frame = int(rng.choice([4096, 30000, 65536, 150000]))
+    image = refwriter.write(data, LZ4, int(rng.choice([0, 3, 9])), frame, int(rng.choice([frame, 4093])))
+    with OraclePort(image) as op:
+        assert op.decode_all().tobytes() == data
+        for codec, mis in ((1, 0), (102, 0), (102, 13), (103, 7)):
+            out, status = emu_api.decode_all(emu, image, codec, op.c_off, op.d_off, ctas=1, misalign=mis)
+            assert (status == 0).all(), (codec, status)
+            assert out.tobytes() == data, codec
