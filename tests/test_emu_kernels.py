@@ -263,3 +263,45 @@ def test_emulated_lz4_kernels_on_random_mixtures(emu, seed):
             out, status = emu_api.decode_all(emu, image, codec, op.c_off, op.d_off, ctas=1, misalign=mis)
             assert (status == 0).all(), (codec, status)
             assert out.tobytes() == data, codec
+
+
+@pytest.mark.parametrize("seed,level", [(1, 1), (2, 3), (3, 19), (4, -3)])
+def test_emulated_zstd_kernel_on_random_mixtures(emu, seed, level):
+    """Same property for the zstd kernel (raw / RLE / compressed blocks, predefined / RLE / compressed / repeat tables, 1- and
+    4-stream and treeless literals all occur in such mixtures), with and without per-job limits."""
+    from datagen import refwriter, zsyn
+    from oracle.pyapi import ZSTD, have_reference
+    if not have_reference():
+        pytest.skip("inputs come from the reference writer (oracle/_ref)")
+    rng = np.random.Generator(np.random.PCG64(2000 + seed))
+    text = zsyn.gen(120000, seed=seed)
+    parts, total = [], 0
+    while total < 180000:
+        kind, n = int(rng.integers(0, 5)), int(rng.integers(1, 12000))
+        if kind == 0:
+            o = int(rng.integers(0, len(text) - n)); p = text[o:o + n]
+        elif kind == 1:
+            p = bytes([int(rng.integers(0, 256))]) * n
+        elif kind == 2:
+            p = rng.integers(0, 256, n, dtype=np.uint8).tobytes()
+        elif kind == 3:
+            per = rng.integers(0, 256, int(rng.integers(1, 40)), dtype=np.uint8).tobytes(); p = (per * (n // len(per) + 1))[:n]
+        else:
+            p = rng.integers(97, 100, n, dtype=np.uint8).tobytes()
+        parts.append(p); total += len(p)
+    data = b"".join(parts)
+    frame = int(rng.choice([20000, 70000, 140000]))
+    image = refwriter.write(data, ZSTD, level, frame, int(rng.choice([frame, 4093])))
+    with OraclePort(image) as op:
+        good = op.decode_all()
+        assert good.tobytes() == data
+        out, status = emu_api.decode_all(emu, image, op.codec, op.c_off, op.d_off, ctas=2)
+        assert (status == 0).all(), status
+        assert out.tobytes() == data
+        sizes = np.diff(op.d_off.astype(np.int64))
+        limits = np.array([int(rng.integers(1, s + 1)) for s in sizes], dtype=np.uint32)
+        out, status = emu_api.decode_all(emu, image, op.codec, op.c_off, op.d_off, ctas=2, limits=limits)
+        assert (status == 0).all(), status
+        for f, s in enumerate(sizes):
+            d0 = int(op.d_off[f])
+            assert (out[d0:d0 + int(limits[f])] == good[d0:d0 + int(limits[f])]).all(), f
