@@ -49,7 +49,9 @@
 #ifndef ZSK_LZ4L_DEPTH
 #define ZSK_LZ4L_DEPTH 2u                 /* trips between parse and execute of a micro-op (1..3) */
 #endif
-#define ZSK_LZ4L_SLOTS 4u                 /* staging slots (DEPTH + 1, power of two) */
+#ifndef ZSK_LZ4L_SLOTS
+#define ZSK_LZ4L_SLOTS 4u                 /* staging slots (>= DEPTH + 1, power of two) */
+#endif
 #ifndef ZSK_LZ4L_WARPS
 #define ZSK_LZ4L_WARPS 2u
 #endif
