@@ -828,7 +828,7 @@ static ssize_t pread_locked(zseek_reader_t *r, void *buf, size_t count, size_t o
             prefetch_start(r, call_data);
         } else if (!fill_window(r, f, hi, !on_device, call_data, errbuf))
             return -1;
-        r->ra_next = MAX(hi, r->pf_active ? r->pf_lo : hi);
+        r->ra_next = hi;
         if (!on_device) {
             memcpy(buf, mirror_half(r, r->mir_cur) + (offset - r->d_off[r->mir_lo]), n);
             return (ssize_t)n;
