@@ -507,7 +507,10 @@ static __device__ int zsk_zstd_block(zsk_zstd_smem &S, const uint8_t *__restrict
                     const uint32_t first = c * ZSK_SEQ_CHUNK;
                     const uint32_t cnt = min(nseq - first, (uint32_t)ZSK_SEQ_CHUNK);
                     if (lane == 0 && !st) {
-                        for (uint32_t i = 0; i < cnt; i++) {
+                        /* the block's very last sequence reads no state bits: walk all but that one with the update, then it */
+                        const uint32_t nwalk = (first + cnt == nseq) ? cnt - 1u : cnt;
+                        uint32_t i = 0;
+                        for (; i < nwalk; i++) {
                             const uint32_t el = S.fse_ll[sl], eo = S.fse_of[so], em = S.fse_ml[sm];
                             dstq[i][0] = sl | (so << 10) | (sm << 20);
                             dstq[i][1] = (uint32_t)b.pos;
@@ -515,17 +518,23 @@ static __device__ int zsk_zstd_block(zsk_zstd_smem &S, const uint8_t *__restrict
                              * the three extra-bit counts (<= 63) stay inside their fields */
                             const uint32_t pk = (el >> 10) + (eo >> 10) + (em >> 10);
                             b.pos -= (int32_t)((pk >> 6) & 0x7fu);
-                            if (first + i + 1 < nseq) {
-                                /* the state bits of LL, ML, OF are adjacent (LL highest): one field of <= 26 bits, then split */
-                                const uint32_t nm = zsk_entry_nb(em), no = zsk_entry_nb(eo), nb = pk & 0x3fu;
-                                zsk_bits_ensure(b, (int32_t)nb);
-                                const uint32_t v = zsk_bits_take(b, nb);
-                                so = (eo & 0x3ffu) + (v & ((1u << no) - 1u));
-                                sm = (em & 0x3ffu) + ((v >> no) & ((1u << nm) - 1u));
-                                sl = (el & 0x3ffu) + (v >> (no + nm));
-                            }
-                            if (b.pos < 0) { st = ZSK_ST_BITSTREAM; break; }
+                            /* the state bits of LL, ML, OF are adjacent (LL highest): one field of <= 26 bits, then split */
+                            const uint32_t nm = zsk_entry_nb(em), no = zsk_entry_nb(eo), nb = pk & 0x3fu;
+                            zsk_bits_ensure(b, (int32_t)nb);
+                            const uint32_t v = zsk_bits_take(b, nb);
+                            so = (eo & 0x3ffu) + (v & ((1u << no) - 1u));
+                            sm = (em & 0x3ffu) + ((v >> no) & ((1u << nm) - 1u));
+                            sl = (el & 0x3ffu) + (v >> (no + nm));
                         }
+                        if (i < cnt) {
+                            const uint32_t el = S.fse_ll[sl], eo = S.fse_of[so], em = S.fse_ml[sm];
+                            dstq[i][0] = sl | (so << 10) | (sm << 20);
+                            dstq[i][1] = (uint32_t)b.pos;
+                            b.pos -= (int32_t)((((el >> 10) + (eo >> 10) + (em >> 10)) >> 6) & 0x7fu);
+                        }
+                        /* an over-read leaves pos negative for good (reads past the start yield zeros, states stay inside their
+                         * tables), so one check per chunk is enough */
+                        if (b.pos < 0) st = ZSK_ST_BITSTREAM;
                         if (!st && c + 1 == nchunks && b.pos != 0) st = ZSK_ST_BITSTREAM;
                     }
                     const int st_a = __shfl_sync(ZSK_FULL, st, 0);
