@@ -503,14 +503,17 @@ static bool decode_into_cache(zseek_reader_t *r, uint32_t n, const uint32_t *nee
     if (n == 0)
         return true;
     r->sorted_lo = r->sorted_hi = 0; /* the job list is about to be overwritten */
+    uint64_t dsum = 0;
     for (uint32_t i = 0; i < n; i++) {
         const uint32_t f = r->h_job_ids[i];
         int32_t s = cache_take(r, f);
         r->h_job_offs[i] = (uint64_t)((size_t)s * r->slot_size);
         r->h_job_limits[i] = need ? need[f] : 0xffffffffu;
+        dsum += r->d_off[f + 1] - r->d_off[f];
     }
     zsk_decode_args a;
     fill_decode_args(r, &a);
+    a.dsize_sum = dsum;
     a.frame_ids = r->g_job_ids;
     a.dst_offs = r->g_job_offs;
     a.dst = r->g_slab + ZSK_PAD_FRONT;
@@ -971,6 +974,7 @@ static bool decode_range_device(zseek_reader_t *r, uint64_t lo, uint64_t hi, uin
     a.first_frame = (uint32_t)lo;
     a.njobs = (uint32_t)(hi - lo);
     a.status = r->g_job_status;
+    a.dsize_sum = r->d_off[hi] - r->d_off[lo];
     if (r->sort_min && hi - lo >= (r->codec == ZSK_CODEC_LZ4 ? r->sort_min : r->sort_min_zstd)) {
         if (r->sorted_lo != lo || r->sorted_hi != hi) {
             order_jobs_by_size(r, lo, hi);
@@ -1150,6 +1154,7 @@ static bool stream_frames_begin(zseek_reader_t *r, uint64_t lo, uint64_t hi, uin
         da.njobs = (uint32_t)(b - a);
         da.status = r->g_job_status + (a - lo);
         const size_t nbytes = (size_t)(r->d_off[b] - r->d_off[a]);
+        da.dsize_sum = nbytes;
         zsk_cuda_trace_mark(r->cx, ZSK_STREAM_H2D, "h2d queued up to chunk", k + 1);
         zsk_cuda_trace_mark(r->cx, ZSK_STREAM_COMPUTE, "decode begin", k);
         if (zsk_cuda_launch_decode(r->cx, r->codec, &da, ZSK_STREAM_COMPUTE) ||

@@ -27,7 +27,9 @@ enum zsk_status {
     ZSK_ST_UNSUPPORTED = 8, /* dictionary id */
     ZSK_ST_SIZE = 9,        /* frame decodes to fewer bytes than the seek table's dSize */
     ZSK_ST_CHECKSUM = 10,   /* header / block / content checksum of the frame does not match */
-    ZSK_ST_STOPPED = 100    /* kernel-internal: the job's limit was reached (reported as ZSK_ST_OK) */
+    ZSK_ST_STOPPED = 100,   /* kernel-internal: the job's limit was reached (reported as ZSK_ST_OK) */
+    ZSK_ST_DEFERRED = 101   /* kernel-internal: the zstd pipeline handed the frame to the one-CTA-per-frame kernel that runs
+                             * last in the same launch (scratch pools too small for it, or an offset beyond 2^28) */
 };
 
 /* Device buffers handed to the kernels must be readable ZSK_PAD_FRONT bytes before and ZSK_PAD_BACK
@@ -59,6 +61,9 @@ typedef struct zsk_decode_args {
     const uint32_t *limits;     /* optional [njobs]: job i may stop once limits[i] bytes of its frame are decoded (a batch of
                                  * small reads needs only the prefix of a frame up to its last requested byte, like the
                                  * reference's streaming no-cache path, src/decompress.c:419-454); NULL = whole frames */
+    uint64_t dsize_sum;         /* sum of the jobs' decompressed sizes (sizes the zstd pipeline's scratch pools); 0 = unknown */
+    const uint32_t *job_list;   /* launch-layer internal: when set, only jobs job_list[0 .. *job_list_count) are run */
+    const unsigned long long *job_list_count;
 } zsk_decode_args;
 
 /* K1: batched offset -> frame lookup (semantics of reference src/seek_table.c:187-202 + decompress.c:445) */

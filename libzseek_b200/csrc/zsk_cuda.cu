@@ -13,7 +13,7 @@
 #include "zsk_lz4.cuh"
 #include "zsk_lz4_lane.cuh"
 #include "zsk_lz4_lane2.cuh"
-#include "zsk_zstd.cuh"
+#include "zsk_zstd_pipe.cuh"
 #include "zsk_seek.cuh"
 
 #define ZSK_NCOUNTERS 64
@@ -30,8 +30,21 @@ struct zsk_cuda_ctx {
     const char *k_name;                  /* name of the most recent decode kernel */
     uint32_t *counters;                  /* ZSK_NCOUNTERS work counters, used round-robin */
     unsigned counter_next;
-    uint8_t *scratch;                    /* zstd literal scratch for zstd_ctas CTAs */
+    uint8_t *scratch;                    /* literal scratch of the one-CTA-per-frame zstd kernel (deferred frames only), zstd_ctas CTAs; lazily allocated */
     int zstd_ctas, lz4_ctas;
+    /* zstd pipeline (zsk_zstd_pipe.cuh): scratch pools grown on demand, per-launch counter blocks used round-robin */
+    zsk_zframe *zframes;
+    uint32_t *zdeferred;
+    size_t zjobs_cap;
+    zsk_zblock *zblocks;
+    uint64_t *zseqs;
+    uint8_t *zlits;
+    size_t zblocks_cap, zseqs_cap, zlits_cap;
+    unsigned long long *zctr;            /* ZSK_NCOUNTERS blocks of ZSK_ZC_N counters */
+    unsigned zctr_next;
+    int zfse_ctas, zhuf_ctas, zexec_ctas;
+    uint64_t zwave_bytes;                /* ZSEEK_B200_ZSTD_WAVE_MB (default 4096) */
+    int zstd_legacy;                     /* ZSEEK_B200_ZSTD_LEGACY=1: every frame goes to the one-CTA-per-frame kernel (A/B runs) */
     int lz4_group;                       /* lanes per LZ4 frame (ZSEEK_B200_LZ4_GROUP: 4, 8, 16 or 32) */
     int lz4_lane_ctas;                   /* resident CTAs of the lane-per-frame kernel */
     int lz4_lane2, lz4_lane2_ctas;       /* ZSEEK_B200_LZ4_LANE2=1: the two-micro-ops-per-trip variant */
@@ -113,6 +126,28 @@ int zsk_cuda_ctx_create(int device, zsk_cuda_ctx **out, char *err, size_t errlen
         if (v >= 1 && v < per_sm) per_sm = v;
     }
     cx->zstd_ctas = per_sm * cx->sm_count;
+    if (const char *g = getenv("ZSEEK_B200_ZSTD_LEGACY")) cx->zstd_legacy = atoi(g);
+    cx->zwave_bytes = (uint64_t)4096 << 20;
+    if (const char *g = getenv("ZSEEK_B200_ZSTD_WAVE_MB")) {
+        const unsigned long long v = strtoull(g, NULL, 10);
+        if (v >= 1) cx->zwave_bytes = (uint64_t)v << 20;
+    }
+    CK0(cudaFuncSetAttribute(zsk_zstd_fse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ZSK_ZFSE_SMEM));
+    CK0(cudaFuncSetAttribute(zsk_zstd_huf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ZSK_ZHUF_SMEM));
+    CK0(cudaFuncSetAttribute(zsk_zstd_exec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ZSK_ZX_SMEM));
+    CK0(cudaFuncSetAttribute(zsk_zstd_huf_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    CK0(cudaFuncSetAttribute(zsk_zstd_exec_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    CK0(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, zsk_zstd_fse_kernel, ZSK_ZFSE_THREADS, ZSK_ZFSE_SMEM));
+    cx->zfse_ctas = (per_sm < 1 ? 1 : per_sm) * cx->sm_count;
+    CK0(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, zsk_zstd_huf_kernel, 32, ZSK_ZHUF_SMEM));
+    cx->zhuf_ctas = (per_sm < 1 ? 1 : per_sm) * cx->sm_count;
+    CK0(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, zsk_zstd_exec_kernel, 32, ZSK_ZX_SMEM));
+    if (const char *g = getenv("ZSEEK_B200_ZEXEC_CTAS_PER_SM")) { /* tuning knob: resident executor warps per SM */
+        int v = atoi(g);
+        if (v >= 1 && v < per_sm) per_sm = v;
+    }
+    cx->zexec_ctas = (per_sm < 1 ? 1 : per_sm) * cx->sm_count;
+    CK0(cudaMalloc((void **)&cx->zctr, ZSK_NCOUNTERS * ZSK_ZC_N * sizeof(unsigned long long)));
     cx->lz4_group = 401;                 /* 401 = batch kernel (warp per frame, default); 1 = lock-step kernel (8 lanes per frame) */
     if (const char *g = getenv("ZSEEK_B200_LZ4_GROUP")) {
         int v = atoi(g);
@@ -151,7 +186,6 @@ int zsk_cuda_ctx_create(int device, zsk_cuda_ctx **out, char *err, size_t errlen
     if (const char *g = getenv("ZSEEK_B200_LZ4_LANE2")) cx->lz4_lane2 = atoi(g);
     cx->lz4_lane_min = 40960;             /* measured crossover: 32,768 frames 11.6 ms (warp per frame) vs 14.1 ms (lane per frame), 49,152 frames 18.6 vs 15.9 ms */
     if (const char *g = getenv("ZSEEK_B200_LZ4_LANE_MIN")) cx->lz4_lane_min = (unsigned)strtoul(g, NULL, 10); /* 0 = always, huge = never */
-    CK0(cudaMalloc((void **)&cx->scratch, (size_t)cx->zstd_ctas * ZSK_LIT_SCRATCH + ZSK_PAD_BACK));
     if (const char *g = getenv("ZSEEK_B200_TRACE")) cx->trace = atoi(g);
     if (cx->trace)
         for (int i = 0; i < ZSK_NTRACE; i++) CK0(cudaEventCreate(&cx->trace_ev[i]));
@@ -176,6 +210,7 @@ void zsk_cuda_ctx_destroy(zsk_cuda_ctx *cx)
     cudaEventDestroy(cx->k1);
     cudaFree(cx->counters);
     cudaFree(cx->scratch);
+    cudaFree(cx->zframes); cudaFree(cx->zdeferred); cudaFree(cx->zblocks); cudaFree(cx->zseqs); cudaFree(cx->zlits); cudaFree(cx->zctr);
     free(cx);
 }
 
@@ -311,6 +346,74 @@ static int next_counter(zsk_cuda_ctx *cx, int stream, uint32_t **out)
     return 0;
 }
 
+/* (re)allocates *p to hold `need` bytes; growth is geometric.  cudaFree waits for everything in flight on the device. */
+static int grow_pool(zsk_cuda_ctx *cx, void **p, size_t *cap_bytes, size_t need)
+{
+    if (need <= *cap_bytes) return 0;
+    size_t want = need > 2 * *cap_bytes ? need : 2 * *cap_bytes;
+    if (*p) CK(cx, cudaFree(*p));
+    *p = NULL;
+    *cap_bytes = 0;
+    if (cudaMalloc(p, want) != cudaSuccess) {
+        cudaGetLastError();
+        want = need;
+        CK(cx, cudaMalloc(p, want));
+    }
+    *cap_bytes = want;
+    return 0;
+}
+
+/* zstd: index -> FSE sequences + Huffman literals -> execution -> (deferred frames) one-CTA-per-frame kernel */
+static int launch_zstd_pipeline(zsk_cuda_ctx *cx, zsk_decode_args a, cudaStream_t s, int stream)
+{
+    const size_t njobs = a.njobs;
+    const uint64_t dsum = a.dsize_sum ? a.dsize_sum : (uint64_t)njobs << 20;
+    int rc;
+    if (!cx->scratch) /* deferred frames are rare: one wave of the old kernel is plenty */
+        CK(cx, cudaMalloc((void **)&cx->scratch, (size_t)cx->sm_count * ZSK_LIT_SCRATCH + ZSK_PAD_BACK));
+    if (njobs > cx->zjobs_cap) {
+        size_t cap_f = cx->zjobs_cap * sizeof(zsk_zframe), cap_d = cx->zjobs_cap * sizeof(uint32_t);
+        if ((rc = grow_pool(cx, (void **)&cx->zframes, &cap_f, njobs * sizeof(zsk_zframe)))) return rc;
+        if ((rc = grow_pool(cx, (void **)&cx->zdeferred, &cap_d, njobs * sizeof(uint32_t)))) return rc;
+        cx->zjobs_cap = cap_f / sizeof(zsk_zframe) < cap_d / sizeof(uint32_t) ? cap_f / sizeof(zsk_zframe) : cap_d / sizeof(uint32_t);
+    }
+    /* pool sizes for typical data: one block per 2 KiB of output, one sequence per 4 bytes, 3/4 of the output as
+     * Huffman literals; frames beyond that are deferred to the old kernel by P0 */
+    const size_t want_blocks = (size_t)(dsum / 2048) + 4 * njobs + 64;
+    const size_t want_seqs = (size_t)(dsum / 4) + 64 * njobs + 1024;
+    const size_t want_lits = (size_t)(dsum / 4 * 3) + 64 * njobs + 4096;
+    size_t cap_b = cx->zblocks_cap * sizeof(zsk_zblock), cap_s = cx->zseqs_cap * sizeof(uint64_t), cap_l = cx->zlits_cap ? cx->zlits_cap + ZSK_PAD_BACK : 0;
+    if ((rc = grow_pool(cx, (void **)&cx->zblocks, &cap_b, want_blocks * sizeof(zsk_zblock)))) return rc;
+    if ((rc = grow_pool(cx, (void **)&cx->zseqs, &cap_s, want_seqs * sizeof(uint64_t)))) return rc;
+    if ((rc = grow_pool(cx, (void **)&cx->zlits, &cap_l, want_lits + ZSK_PAD_BACK))) return rc;
+    cx->zblocks_cap = cap_b / sizeof(zsk_zblock);
+    cx->zseqs_cap = cap_s / sizeof(uint64_t);
+    cx->zlits_cap = cap_l - ZSK_PAD_BACK;
+
+    zsk_zpipe_args z;
+    z.a = a;
+    z.frames = cx->zframes; z.blocks = cx->zblocks; z.seqs = cx->zseqs; z.lits = cx->zlits;
+    z.blocks_cap = cx->zblocks_cap; z.seqs_cap = cx->zseqs_cap; z.lits_cap = cx->zlits_cap;
+    z.ctr = cx->zctr + (size_t)(cx->zctr_next++ % ZSK_NCOUNTERS) * ZSK_ZC_N;
+    z.deferred = cx->zdeferred;
+    CK(cx, cudaMemsetAsync(z.ctr, 0, ZSK_ZC_N * sizeof(unsigned long long), s));
+    zsk_zstd_index_kernel<<<(unsigned)((njobs + 127) / 128), 128, 0, s>>>(z);
+    zsk_zstd_fse_kernel<<<cx->zfse_ctas, ZSK_ZFSE_THREADS, ZSK_ZFSE_SMEM, s>>>(z);
+    zsk_zstd_huf_kernel<<<cx->zhuf_ctas, 32, ZSK_ZHUF_SMEM, s>>>(z);
+    unsigned xctas = njobs < (size_t)cx->zexec_ctas ? (unsigned)njobs : (unsigned)cx->zexec_ctas;
+    zsk_zstd_exec_kernel<<<xctas, 32, ZSK_ZX_SMEM, s>>>(z);
+    /* frames P0 / P1a handed over (normally none: the CTAs find an empty list and leave) */
+    zsk_decode_args d = a;
+    d.job_list = z.deferred;
+    d.job_list_count = z.ctr + ZSK_ZC_DEFERRED;
+    d.scratch = cx->scratch;
+    if ((rc = next_counter(cx, stream, &d.work_counter))) return rc;
+    unsigned dctas = njobs < (size_t)cx->sm_count ? (unsigned)njobs : (unsigned)cx->sm_count;
+    zsk_zstd_decode_kernel<<<dctas, ZSK_ZSTD_CTA_THREADS, 0, s>>>(d);
+    cx->launches += 4;
+    return 0;
+}
+
 int zsk_cuda_launch_decode(zsk_cuda_ctx *cx, int codec, const zsk_decode_args *args, int stream)
 {
     if (args->njobs == 0) return 0;
@@ -318,7 +421,8 @@ int zsk_cuda_launch_decode(zsk_cuda_ctx *cx, int codec, const zsk_decode_args *a
     zsk_decode_args a = *args;
     int rc = next_counter(cx, stream, &a.work_counter);
     if (rc) return rc;
-    a.scratch = cx->scratch;
+    a.job_list = NULL;
+    a.job_list_count = NULL;
     cudaStream_t s = cx->streams[stream];
     CK(cx, cudaEventRecord(cx->k0, s));
     if (codec == ZSK_CODEC_LZ4 && cx->lz4_group == 401 && a.njobs >= cx->lz4_lane_min) {
@@ -348,10 +452,31 @@ int zsk_cuda_launch_decode(zsk_cuda_ctx *cx, int codec, const zsk_decode_args *a
         case 116: zsk_lz4_decode_lockstep_kernel<16><<<ctas, ZSK_LZ4_CTA_THREADS, 0, s>>>(a); break;
         default: zsk_lz4_decode_lockstep_kernel<8><<<ctas, ZSK_LZ4_CTA_THREADS, 0, s>>>(a); break;
         }
-    } else if (codec == ZSK_CODEC_ZSTD) {
+    } else if (codec == ZSK_CODEC_ZSTD && cx->zstd_legacy) {
+        if (!cx->scratch) CK(cx, cudaMalloc((void **)&cx->scratch, (size_t)cx->zstd_ctas * ZSK_LIT_SCRATCH + ZSK_PAD_BACK));
+        a.scratch = cx->scratch;
         unsigned ctas = a.njobs < (unsigned)cx->zstd_ctas ? a.njobs : (unsigned)cx->zstd_ctas;
         zsk_zstd_decode_kernel<<<ctas, ZSK_ZSTD_CTA_THREADS, 0, s>>>(a);
         cx->k_name = "zsk_zstd_decode_kernel";
+    } else if (codec == ZSK_CODEC_ZSTD) {
+        /* waves of at most zwave_bytes of output share one set of scratch pools (2.75 bytes of scratch per output byte) */
+        const uint64_t dsum = a.dsize_sum ? a.dsize_sum : (uint64_t)a.njobs << 20;
+        const uint32_t total = a.njobs;
+        uint32_t per_wave = total;
+        if (dsum > cx->zwave_bytes) per_wave = (uint32_t)((double)total * (double)cx->zwave_bytes / (double)dsum) + 1u;
+        for (uint32_t j0 = 0; j0 < total; j0 += per_wave) {
+            zsk_decode_args w = a;
+            w.njobs = total - j0 < per_wave ? total - j0 : per_wave;
+            w.first_frame = a.first_frame + j0;
+            if (a.frame_ids) w.frame_ids = a.frame_ids + j0;
+            if (a.dst_offs) w.dst_offs = a.dst_offs + j0;
+            if (a.limits) w.limits = a.limits + j0;
+            w.status = a.status + j0;
+            w.dsize_sum = (uint64_t)((double)dsum * (double)w.njobs / (double)total) + 1u;
+            rc = launch_zstd_pipeline(cx, w, s, stream);
+            if (rc) return rc;
+        }
+        cx->k_name = "zsk_zstd_exec_kernel";
     } else {
         snprintf(cx->err, sizeof(cx->err), "unknown codec %d", codec);
         return -1;

@@ -246,10 +246,10 @@ static __device__ int zsk_seq_table(uint32_t *tab, int32_t *log_io, int mode, co
 
 /* ---- Huffman tree description -> weights[] (incl. the implicit last one).  Single thread.
  * Returns bytes consumed (>0) or -status; sets *nw and *max_bits. */
-static __device__ int zsk_huf_read_weights(zsk_zstd_smem &S, const uint8_t *p, uint32_t n, int *nw_out, int *max_bits_out)
+static __device__ int zsk_huf_read_weights(uint8_t *w, uint16_t *huf_start, uint32_t *wtab, int16_t *probs_w, uint16_t *next_w,
+                                           const uint8_t *p, uint32_t n, int *nw_out, int *max_bits_out)
 {
     if (n < 1) return -ZSK_ST_TRUNC;
-    uint8_t *w = S.weights;
     int nw = 0;
     const uint32_t hb = ZSK_LDG(p);
     uint32_t used;
@@ -265,9 +265,9 @@ static __device__ int zsk_huf_read_weights(zsk_zstd_smem &S, const uint8_t *p, u
     } else {
         if (hb == 0 || 1 + hb > n) return -ZSK_ST_TRUNC;
         int nsym, log;
-        int hdr = zsk_fse_read_ncount(p + 1, hb, 6, 12, S.probs_w, &nsym, &log);
+        int hdr = zsk_fse_read_ncount(p + 1, hb, 6, 12, probs_w, &nsym, &log);
         if (hdr < 0) return hdr;
-        int r = zsk_fse_build(S.wtab, S.probs_w, nsym, log, S.next_w);
+        int r = zsk_fse_build(wtab, probs_w, nsym, log, next_w);
         if (r) return -r;
         if ((uint32_t)hdr >= hb) return -ZSK_ST_TRUNC;
         zsk_bits b;
@@ -276,14 +276,14 @@ static __device__ int zsk_huf_read_weights(zsk_zstd_smem &S, const uint8_t *p, u
         uint32_t s1 = zsk_bits_read(b, (uint32_t)log), s2 = zsk_bits_read(b, (uint32_t)log);
         for (;;) {
             if (nw > 253) return -ZSK_ST_TABLE;
-            uint32_t e1 = S.wtab[s1];
+            uint32_t e1 = wtab[s1];
             w[nw++] = (uint8_t)e1;
             s1 = (e1 >> 16) + zsk_bits_read(b, (e1 >> 8) & 0xff);
-            if (b.pos < 0) { w[nw++] = (uint8_t)S.wtab[s2]; break; }
-            uint32_t e2 = S.wtab[s2];
+            if (b.pos < 0) { w[nw++] = (uint8_t)wtab[s2]; break; }
+            uint32_t e2 = wtab[s2];
             w[nw++] = (uint8_t)e2;
             s2 = (e2 >> 16) + zsk_bits_read(b, (e2 >> 8) & 0xff);
-            if (b.pos < 0) { w[nw++] = (uint8_t)S.wtab[s1]; break; }
+            if (b.pos < 0) { w[nw++] = (uint8_t)wtab[s1]; break; }
         }
         used = 1 + hb;
     }
@@ -307,7 +307,7 @@ static __device__ int zsk_huf_read_weights(zsk_zstd_smem &S, const uint8_t *p, u
     for (int s = 0; s < nw; s++) {
         if (!w[s]) continue;
         int nbits = max_bits + 1 - w[s];
-        S.huf_start[s] = (uint16_t)idx[nbits];
+        huf_start[s] = (uint16_t)idx[nbits];
         idx[nbits] += 1u << (max_bits - nbits);
     }
     *nw_out = nw;
@@ -413,7 +413,7 @@ static __device__ int zsk_zstd_block(zsk_zstd_smem &S, const uint8_t *__restrict
             if (ltype == 2) {
                 int used = 0;
                 if (lane == 0) {
-                    used = zsk_huf_read_weights(S, q, qn, &nw, &max_bits);
+                    used = zsk_huf_read_weights(S.weights, S.huf_start, S.wtab, S.probs_w, S.next_w, q, qn, &nw, &max_bits);
                     if (used < 0) st = -used; else S.log_huf = max_bits;
                 }
                 __syncwarp(); /* weights[], huf_start[], log_huf visible to the warp */
@@ -743,8 +743,11 @@ __global__ void __launch_bounds__(ZSK_ZSTD_CTA_THREADS, ZSK_ZSTD_MIN_CTAS) zsk_z
         __syncthreads();
         if (threadIdx.x == 0) S.job = atomicAdd(a.work_counter, 1u);
         __syncthreads();
-        const uint32_t job = S.job;
-        if (job >= a.njobs) break;
+        uint32_t job = S.job;
+        if (a.job_list) { /* the pipeline's deferred frames only */
+            if (job >= (uint32_t)*a.job_list_count) break;
+            job = a.job_list[job];
+        } else if (job >= a.njobs) break;
         const uint32_t f = a.frame_ids ? a.frame_ids[job] : a.first_frame + job;
         const uint64_t c0 = a.c_off[f], c1 = a.c_off[f + 1], d0 = a.d_off[f], d1 = a.d_off[f + 1];
         const uint8_t *src = a.comp + (c0 - a.comp_base);

@@ -6,10 +6,49 @@
 #include "../../libzseek_b200/csrc/zsk_lz4.cuh"
 #include "../../libzseek_b200/csrc/zsk_lz4_lane.cuh"
 #include "../../libzseek_b200/csrc/zsk_lz4_lane2.cuh"
-#include "../../libzseek_b200/csrc/zsk_zstd.cuh"
+#include "../../libzseek_b200/csrc/zsk_zstd_pipe.cuh"
 #include "../../libzseek_b200/csrc/zsk_seek.cuh"
 
+static uint32_t g_emu_deferred = 0;
+
+/* The shipped zstd path: the four pipeline kernels, then the one-CTA-per-frame kernel over the deferred list.
+ * tiny_pools: pools far too small, so that P0 defers most frames (exercises the hand-over). */
+static void emu_zstd_pipeline(zsk_decode_args a, uint32_t njobs, uint32_t ctas, const uint64_t *d_off, uint32_t first_frame,
+                              const uint32_t *frame_ids, bool tiny_pools)
+{
+    uint64_t dsum = 0;
+    for (uint32_t j = 0; j < njobs; j++) {
+        const uint32_t f = frame_ids ? frame_ids[j] : first_frame + j;
+        dsum += d_off[f + 1] - d_off[f];
+    }
+    zsk_zpipe_args z;
+    z.a = a;
+    z.blocks_cap = tiny_pools ? 3 : dsum / 2048 + 4 * njobs + 64;
+    z.seqs_cap = tiny_pools ? 2000 : dsum / 4 + 64 * njobs + 1024;
+    z.lits_cap = tiny_pools ? 20000 : dsum / 4 * 3 + 64 * njobs + 4096;
+    std::vector<zsk_zframe> frames(njobs + 1);
+    std::vector<zsk_zblock> blocks(z.blocks_cap + 1);
+    std::vector<uint64_t> seqs(z.seqs_cap + 1, 0xEEEEEEEEEEEEEEEEull);
+    std::vector<uint8_t> lits(z.lits_cap + ZSK_PAD_BACK, 0xEE);
+    std::vector<uint32_t> deferred(njobs + 1);
+    unsigned long long ctr[ZSK_ZC_N] = { 0 };
+    z.frames = frames.data(); z.blocks = blocks.data(); z.seqs = seqs.data(); z.lits = lits.data();
+    z.ctr = ctr; z.deferred = deferred.data();
+    emu::launch(dim3((njobs + 127) / 128), dim3(128), 0, [&] { zsk_zstd_index_kernel(z); });
+    emu::launch(dim3(ctas), dim3(ZSK_ZFSE_THREADS), ZSK_ZFSE_SMEM, [&] { zsk_zstd_fse_kernel(z); });
+    emu::launch(dim3(ctas), dim3(32), ZSK_ZHUF_SMEM, [&] { zsk_zstd_huf_kernel(z); });
+    emu::launch(dim3(ctas), dim3(32), ZSK_ZX_SMEM, [&] { zsk_zstd_exec_kernel(z); });
+    uint32_t counter = 0;
+    zsk_decode_args d = a;
+    d.job_list = z.deferred;
+    d.job_list_count = z.ctr + ZSK_ZC_DEFERRED;
+    d.work_counter = &counter;
+    emu::launch(dim3(ctas), dim3(ZSK_ZSTD_CTA_THREADS), 0, [&] { zsk_zstd_decode_kernel(d); });
+    g_emu_deferred = (uint32_t)ctr[ZSK_ZC_DEFERRED];
+}
+
 extern "C" {
+__attribute__((visibility("default"))) uint32_t emu_last_deferred() { return g_emu_deferred; }
 
 /* comp points at the byte with file offset comp_base; the caller guarantees >= 16 readable bytes
  * before it and >= 64 after the last frame (same contract as the device buffers). */
@@ -24,11 +63,13 @@ void emu_decode(int codec, const uint8_t *comp, uint64_t comp_base, const uint64
     a.c_off = c_off; a.d_off = d_off; a.comp = comp; a.comp_base = comp_base; a.frame_ids = frame_ids;
     a.dst_offs = dst_offs; a.dst = dst; a.dst_base = dst_base; a.first_frame = first_frame; a.njobs = njobs;
     a.status = status; a.work_counter = &counter; a.scratch = scratch.data(); a.limits = limits;
+    a.dsize_sum = 0; a.job_list = nullptr; a.job_list_count = nullptr;
     if (codec == 1) emu::launch(dim3(ctas), dim3(ZSK_LZ4_CTA_THREADS), 0, [&] { zsk_lz4_decode_batch_kernel(a); });           /* shipped default */
     else if (codec == 101) emu::launch(dim3(ctas), dim3(ZSK_LZ4_CTA_THREADS), 0, [&] { zsk_lz4_decode_lockstep_kernel<8>(a); }); /* alternative */
     else if (codec == 103) emu::launch(dim3(ctas), dim3(ZSK_LZ4L_THREADS), ZSK_LZ4L2_SMEM, [&] { zsk_lz4_decode_lane2_kernel(a); }); /* two micro-ops per trip */
     else if (codec == 102) emu::launch(dim3(ctas), dim3(ZSK_LZ4L_THREADS), ZSK_LZ4L_SMEM, [&] { zsk_lz4_decode_lane_kernel(a); });  /* many-frame launches */
-    else emu::launch(dim3(ctas), dim3(ZSK_ZSTD_CTA_THREADS), 0, [&] { zsk_zstd_decode_kernel(a); });
+    else if (codec == 200) emu::launch(dim3(ctas), dim3(ZSK_ZSTD_CTA_THREADS), 0, [&] { zsk_zstd_decode_kernel(a); }); /* one CTA per frame: only deferred frames in the product */
+    else emu_zstd_pipeline(a, njobs, ctas, d_off, first_frame, frame_ids, codec == 201);
 }
 
 __attribute__((visibility("default")))

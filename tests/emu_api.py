@@ -20,6 +20,7 @@ def lib():
                              C.c_void_p, C.c_void_p, C.c_void_p]
     L.emu_gather.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                              C.c_uint64, C.c_uint32]
+    L.emu_last_deferred.restype = C.c_uint32
     return L
 
 

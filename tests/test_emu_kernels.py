@@ -29,6 +29,36 @@ def test_emulated_decode_matches_reference_output(emu, golden, name):
     assert hashlib.sha256(out.tobytes()).hexdigest() == c["input_sha256"]
 
 
+ZSTD_CASES = ["tiny_zstd", "zsyn_zstd3_128k", "zsyn_zstd19_256k", "zsyn_zstd3_mt", "mix_zstd3", "mix_zstd19"]
+
+
+@pytest.mark.parametrize("name", ZSTD_CASES)
+@pytest.mark.parametrize("kernel", [200, 201])
+def test_emulated_zstd_deferred_frames(emu, golden, name, kernel):
+    """200: the one-CTA-per-frame kernel alone (what deferred frames get).  201: the pipeline with scratch pools far too
+    small, so P0 hands most frames over to that kernel inside the same launch."""
+    cases, _ = golden
+    c = cases[name]
+    with OraclePort(c["image"]) as op:
+        out, status = emu_api.decode_all(emu, c["image"], kernel, op.c_off, op.d_off, ctas=2)
+        if kernel == 201 and op.frames > 1 and name != "tiny_zstd":
+            assert emu.emu_last_deferred() > 0
+    assert (status == 0).all(), status
+    assert hashlib.sha256(out.tobytes()).hexdigest() == c["input_sha256"]
+
+
+@pytest.mark.parametrize("misalign", [1, 7, 15, 17, 31])
+@pytest.mark.parametrize("name", ["zsyn_zstd3_128k", "mix_zstd19"])
+def test_emulated_zstd_pipeline_unaligned_output(emu, golden, name, misalign):
+    """The executor's ring is flushed in 16-byte vectors aligned on the GLOBAL address; heads and tails go bytewise."""
+    cases, _ = golden
+    c = cases[name]
+    with OraclePort(c["image"]) as op:
+        out, status = emu_api.decode_all(emu, c["image"], op.codec, op.c_off, op.d_off, ctas=2, misalign=misalign)
+    assert (status == 0).all(), status
+    assert hashlib.sha256(out.tobytes()).hexdigest() == c["input_sha256"]
+
+
 @pytest.mark.parametrize("name", ["zsyn_lz4_64k", "zsyn_lz4_256k_linked", "mix_lz4"])
 def test_emulated_lockstep_lz4_kernel(emu, golden, name):
     """The alternative LZ4 kernel (8-lane groups in lock-step, ZSEEK_B200_LZ4_GROUP=1) stays correct too."""
@@ -70,7 +100,8 @@ def test_emulated_lane_lz4_kernel_unaligned_output(emu, golden, misalign, kernel
     assert hashlib.sha256(out.tobytes()).hexdigest() == c["input_sha256"]
 
 
-@pytest.mark.parametrize("name,codec", [("zsyn_lz4_64k", None), ("zsyn_lz4_64k", 102), ("zsyn_lz4_64k", 103), ("zsyn_zstd3_128k", None)])
+@pytest.mark.parametrize("name,codec", [("zsyn_lz4_64k", None), ("zsyn_lz4_64k", 102), ("zsyn_lz4_64k", 103), ("zsyn_zstd3_128k", None),
+                                        ("zsyn_zstd3_128k", 200), ("zsyn_zstd3_128k", 201)])
 def test_emulated_decode_flags_corrupt_frames(emu, golden, name, codec):
     """Truncation and bit flips must end in a non-zero status, never a hang or an out-of-bounds write."""
     cases, _ = golden
@@ -162,7 +193,8 @@ def test_emulated_lane_lz4_kernel_sequence_shapes(emu, kw):
 
 @pytest.mark.parametrize("name,codec", [("zsyn_lz4_64k", 1), ("zsyn_lz4_64k", 102), ("zsyn_lz4_256k_linked", 102), ("mix_lz4", 1),
                                         ("zsyn_lz4_64k", 103), ("mix_lz4", 103),
-                                        ("zsyn_zstd3_128k", None), ("zsyn_zstd19_256k", None), ("mix_zstd3", None)])
+                                        ("zsyn_zstd3_128k", None), ("zsyn_zstd19_256k", None), ("mix_zstd3", None),
+                                        ("zsyn_zstd3_128k", 200), ("mix_zstd3", 201)])
 def test_emulated_decode_stops_at_job_limits(emu, golden, name, codec):
     """Batches of small reads decode a frame only up to the last byte they need (zsk_decode_args.limits): the prefix
     must be exact, the status OK, and nothing may be written outside the frame."""
