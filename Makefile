@@ -17,7 +17,7 @@ $(SRC)/reader.o: $(SRC)/reader.c $(wildcard $(SRC)/*.h) $(wildcard include/*.h)
 	$(CC) $(CFLAGS) -c $< -o $@
 
 $(OUT): $(SRC)/zsk_cuda.o $(SRC)/reader.o
-	$(NVCC) $(ARCH) -shared -o $@ $^ -lpthread
+	$(NVCC) $(ARCH) -cudart shared -shared -o $@ $^ -lpthread
 
 oracle:
 	$(MAKE) -C oracle
@@ -26,7 +26,7 @@ oracle:
 alt:
 	$(NVCC) $(NVFLAGS) -c $(SRC)/zsk_cuda.cu -o $(SRC)/zsk_cuda_alt.o
 	$(CC) $(CFLAGS) -c $(SRC)/reader.c -o $(SRC)/reader_alt.o
-	$(NVCC) $(ARCH) -shared -o libzseek_b200/libzseek_b200_alt.so $(SRC)/zsk_cuda_alt.o $(SRC)/reader_alt.o -lpthread
+	$(NVCC) $(ARCH) -cudart shared -shared -o libzseek_b200/libzseek_b200_alt.so $(SRC)/zsk_cuda_alt.o $(SRC)/reader_alt.o -lpthread
 
 clean:
 	rm -f $(SRC)/*.o $(OUT)

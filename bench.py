@@ -7,26 +7,38 @@ Workload at every N (config.workload): BASELINE.json configs[1] — LZ4 level 0 
 data, 64 KiB frames, G GiB per GPU (default 4; frame-range sharded, per-GPU work fixed => "weak"),
 whole-file sequential decode.  A "step" = one pass of the hot path over that file.
 
+The corpus is UNIQUE data by default (tile = file size: no frame occurs twice); --tile-mib T builds the
+file from a T-MiB tile instead (SURVEY.md §8d allows tiles >= 1 GiB), and at N = 1 the line carries an
+A/B of the headline on a 512 MiB tile x 8 (`extra.replica_ab`) so the effect of replicas on the
+size-ordered job list of the lane-per-frame LZ4 kernel is on record.
+
   value    whole-job decompressed GB/s with the compressed image already resident in HBM and the
            output going to HBM; timed with CUDA events on the launching stream, max over ranks.
   e2e      same metric through the C-ABI with HOST buffers: compressed image in pinned host memory,
            zseek_b200_read_range into a pinned host buffer, H2D + decode + D2H inside the timed region.
   roofline the LZ4 decode kernel against the measured HBM copy bandwidth (MEASURED_PEAKS.json):
            algorithmic bytes = C + D per launch.
-  cpu_baseline  the unmodified reference (oracle/_ref) on the host cores, one reader per thread.
-  extra    configs[2] (zstd level 3, 256 KiB frames) decode GB/s and the batched random 4 KiB pread
-           rate (configs[3] shape, scaled to the zstd file that is resident), each with its own
-           roofline fraction and CPU figure.
+  cpu_baseline  the unmodified reference (oracle/_ref) on the host cores, one reader per thread;
+           warm-up pass, then median (value) and best of 5.
+  verified_bytes  every byte the timed loops produced is compared with the writer's input after the
+           loop (device compare for HBM outputs, upload + device compare for the e2e host buffer);
+           all 1 M random results are checked (lengths against B1 arithmetic, bytes on the device).
+  extra    configs[2] (zstd-3, 256 KiB frames; value, e2e, roofline), configs[3] at its stated shape
+           (1 M x 4 KiB over a 16 GiB zstd-3 file of 65,536 frames, rank 0), configs[4] (1 MiB frames,
+           LZ4 + zstd-19, 8 GiB per GPU, every rank), the replica A/B, and the same-run bare pinned-copy
+           ceiling the e2e figures are measured against.
 
 --impl reference times the reference's own CPU implementation of the same workload on all host
-cores (rank 0 only) and prints the same line with "impl": "reference".
+cores (rank 0 only; each step decodes the first 1 GiB of the same file) and prints the same line with
+"impl": "reference".
 
-Inputs are produced by the reference CPU writer (north_star) with the tile-and-replicate construction
-of SURVEY.md §8d: a T-MiB zsyn-v1 tile is written once, its compressed frames are replicated.
+Inputs are produced by the reference CPU writer (north_star) once per box and kept under /dev/shm for
+the other arm / the other N of the same round.
 """
 import argparse
 import json
 import os
+import shutil
 import subprocess
 import sys
 import tempfile
@@ -39,6 +51,7 @@ sys.path.insert(0, ROOT)
 
 LZ4, ZSTD = 1, 0
 GB = 1e9
+MIB = 1 << 20
 
 
 def log(*a):
@@ -56,7 +69,7 @@ def measured_peak():
 
 
 def profile_traffic(kernel):
-    """Per-launch DRAM traffic from the committed ncu capture, if one exists for this kernel."""
+    """Per-launch DRAM traffic of this kernel at the bench shape from the committed ncu capture (profiles/traffic.json)."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(p):
         try:
@@ -66,48 +79,79 @@ def profile_traffic(kernel):
     return None
 
 
+def workload_config(args):
+    """config of the JSON line — identical in both arms."""
+    return {"workload": f"BASELINE configs[1]: LZ4 level 0 seekable file, zsyn-v1, 64 KiB frames, "
+                        f"{args.size_gib:g} GiB per GPU, full sequential decode",
+            "tile_mib": args.tile_mib, "unique_data": args.tile_mib * MIB >= int(args.size_gib * (1 << 30))}
+
+
 # ----------------------------------------------------------------------------- inputs
-def build_inputs(args, rank, world):
-    """Returns dict name -> (image ndarray, total decompressed bytes, tile bytes)."""
-    from datagen import refwriter, zsyn
-    tile_bytes = args.tile_mib << 20
-    total = int(args.size_gib * (1 << 30))
-    reps = max(1, total // tile_bytes)
-    cache = os.path.join("/dev/shm" if os.path.isdir("/dev/shm") else tempfile.gettempdir(),
-                         f"zsk_bench_{os.environ.get('MASTER_PORT', 'solo')}_{args.tile_mib}")
-    paths = {k: f"{cache}_{k}.zsk" for k in ("lz4", "zstd3")}
-    done = cache + ".done"
-    if rank == 0 and not os.path.exists(done):
-        t0 = time.time()
-        tile = zsyn.gen_parallel(tile_bytes)
-        log(f"[bench] zsyn-v1 tile {args.tile_mib} MiB generated in {time.time() - t0:.1f}s")
-        t0 = time.time()
-        one = {"lz4": refwriter.write_parallel(tile, LZ4, 0, 65536, piece_frames=1024),
-               "zstd3": refwriter.write_parallel(tile, ZSTD, 3, 262144, strategy=0, piece_frames=256)}
-        log(f"[bench] reference writer: lz4 ratio {tile_bytes / len(one['lz4']):.3f}, zstd3 ratio "
-            f"{tile_bytes / len(one['zstd3']):.3f} in {time.time() - t0:.1f}s")
-        for k, img in one.items():
-            with open(paths[k], "wb") as f:
-                f.write(img)
-        open(done, "w").write("ok")
-    if world > 1:
-        import torch.distributed as dist
-        dist.barrier()
-    out = {}
-    for k in ("lz4", "zstd3"):
-        one = open(paths[k], "rb").read()
-        img = refwriter.replicate(one, reps)
-        out[k] = (np.frombuffer(img, dtype=np.uint8), reps * tile_bytes)
-    return out, cache
+class Corpus:
+    """Files of one round under /dev/shm (or the temp dir): the raw tile and the reference writer's images of it."""
+    C5_LZ4_TILE_MIB = 1024     # configs[4]: 1 MiB frames; LZ4 over the first 1 GiB of the tile, zstd-19 over the first 256 MiB
+    C5_ZSTD_TILE_MIB = 256
 
+    def __init__(self, args):
+        self.args = args
+        self.tile = args.tile_mib * MIB
+        self.total = int(args.size_gib * (1 << 30))
+        assert self.total % self.tile == 0, "--size-gib must be a multiple of --tile-mib"
+        self.reps = self.total // self.tile
+        need = int(self.tile * 2.2) + (2 << 30)
+        base = "/dev/shm" if os.path.isdir("/dev/shm") and shutil.disk_usage("/dev/shm").free > need else tempfile.gettempdir()
+        self.dir = os.path.join(base, f"zsk_bench_r2_{args.tile_mib}")
+        self.c5_lz4_tile = min(self.tile, self.C5_LZ4_TILE_MIB * MIB)
+        self.c5_zstd_tile = min(self.tile, self.C5_ZSTD_TILE_MIB * MIB)
 
-def cleanup_inputs(cache, rank):
-    if rank == 0:
-        for suffix in ("_lz4.zsk", "_zstd3.zsk", ".done"):
-            try:
-                os.remove(cache + suffix)
-            except OSError:
-                pass
+    def path(self, name):
+        return os.path.join(self.dir, name)
+
+    def build(self, need_all=True):
+        """rank 0 only; idempotent."""
+        from datagen import refwriter, zsyn
+        if os.path.exists(self.path("done_all" if need_all else "done_lz4")):
+            return
+        os.makedirs(self.dir, exist_ok=True)
+
+        def put(name, data):
+            with open(self.path(name + ".tmp"), "wb") as f:
+                f.write(data)
+            os.replace(self.path(name + ".tmp"), self.path(name))
+
+        t0 = time.time()
+        if os.path.exists(self.path("raw.bin")):
+            tile = open(self.path("raw.bin"), "rb").read()
+        else:
+            tile = zsyn.gen_parallel(self.tile)
+            put("raw.bin", tile)
+        log(f"[bench] zsyn-v1 tile {self.args.tile_mib} MiB ready in {time.time() - t0:.1f}s")
+        if not os.path.exists(self.path("lz4.zsk")):
+            t0 = time.time()
+            img = refwriter.write_parallel(tile, LZ4, 0, 65536, piece_frames=1024)
+            put("lz4.zsk", img)
+            log(f"[bench] reference writer lz4 64 KiB frames: ratio {self.tile / len(img):.3f} in {time.time() - t0:.1f}s")
+        open(self.path("done_lz4"), "w").write("ok")
+        if not need_all:
+            return
+        jobs = [("zstd3.zsk", ZSTD, 3, 262144, self.tile, 256), ("lz4_1m.zsk", LZ4, 0, MIB, self.c5_lz4_tile, 16),
+                ("zstd19_1m.zsk", ZSTD, 19, MIB, self.c5_zstd_tile, 1)]
+        for name, codec, level, frame, nbytes, piece in jobs:
+            if os.path.exists(self.path(name)):
+                continue
+            t0 = time.time()
+            img = refwriter.write_parallel(tile[:nbytes], codec, level, frame, strategy=0, piece_frames=piece)
+            put(name, img)
+            log(f"[bench] reference writer {name}: ratio {nbytes / len(img):.3f} in {time.time() - t0:.1f}s")
+        open(self.path("done_all"), "w").write("ok")
+
+    def image(self, name, reps):
+        from datagen import refwriter
+        one = open(self.path(name), "rb").read()
+        return np.frombuffer(one if reps == 1 else refwriter.replicate(one, reps), dtype=np.uint8)
+
+    def raw(self):
+        return np.memmap(self.path("raw.bin"), dtype=np.uint8, mode="r")
 
 
 # ----------------------------------------------------------------------------- clocks
@@ -169,20 +213,18 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------- CPU (reference) legs
-def cpu_scan(image, total, threads, repeats=3):
+def cpu_scan_stats(image, sample, threads, runs=5):
+    """Warm-up pass, then `runs` timed passes of the reference over the first `sample` decompressed bytes:
+    -> (median GB/s, best GB/s)."""
     from oracle.pyapi import RefDrive
-    best = None
-    for _ in range(repeats):
-        t, nbytes = RefDrive.scan(image, total, threads, req=1 << 20, cache_size=0, pin=True)
-        assert nbytes == total
-        best = t if best is None else min(best, t)
-    return best
-
-
-def cpu_random(image, offsets, count, threads):
-    from oracle.pyapi import RefDrive
-    t, ops = RefDrive.random(image, offsets, count, threads, cache_size=0, pin=True)
-    return t, ops
+    RefDrive.scan(image, sample, threads, req=1 << 20, cache_size=0, pin=True)
+    ts = []
+    for _ in range(runs):
+        t, nbytes = RefDrive.scan(image, sample, threads, req=1 << 20, cache_size=0, pin=True)
+        assert nbytes == sample
+        ts.append(t)
+    ts.sort()
+    return sample / ts[len(ts) // 2] / GB, sample / ts[0] / GB
 
 
 def gen_offsets(n, total, count, seed=1):
@@ -199,7 +241,9 @@ def run_b200(args, rank, world):
     local = int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
     os.environ["ZSEEK_B200_DEVICE"] = str(local)
-    inputs, cache = build_inputs(args, rank, world)
+    corpus = Corpus(args)
+    if rank == 0:
+        corpus.build()
     peak, peak_src = measured_peak()
 
     def barrier():
@@ -214,201 +258,300 @@ def run_b200(args, rank, world):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    def sum_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
+    def min_over_ranks(x):
+        return -max_over_ranks(-x)
 
-    results = {}
-    launches_total = 0
-    clocks = None
-    for name in ("lz4", "zstd3"):
-        image, total = inputs[name]
-        pinned = torch.from_numpy(image.copy()).pin_memory()       # compressed file image in pinned host memory
+    barrier()
+    tile = corpus.tile
+    raw_dev = torch.from_numpy(np.ascontiguousarray(corpus.raw())).cuda()       # the writer's input, for verification
+
+    def verify_device(dev, nbytes, period):
+        """bytes of dev[:nbytes] equal to the (period-tiled) writer input; compares everything."""
+        ok = 0
+        step = 256 * MIB
+        for o in range(0, nbytes, step):
+            n = min(step, nbytes - o)
+            p = o % period
+            assert p + n <= period, "compare chunks must not straddle the tile (tiles are multiples of 256 MiB, or the file is one tile)"
+            if bool((dev[o:o + n] == raw_dev[p:p + n]).all()):
+                ok += n
+        return ok
+
+    def pcie_ceiling():
+        """bare pinned copies of 1 GiB, same run: (H2D GB/s, D2H GB/s)"""
+        n = 1 << 30
+        h = torch.empty(n, dtype=torch.uint8).pin_memory()
+        d = torch.empty(n, dtype=torch.uint8, device="cuda")
+        out = []
+        for dst, src in ((d, h), (h, d)):
+            dst.copy_(src, non_blocking=True)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(3):
+                dst.copy_(src, non_blocking=True)
+            torch.cuda.synchronize()
+            out.append(3 * n / (time.perf_counter() - t0) / GB)
+        return out
+
+    def decode_leg(image, total, period, steps, warmup, sampler=None):
+        """HBM -> HBM whole-file decode: CUDA-event time of `steps` passes (max over ranks), everything verified."""
+        pinned = torch.from_numpy(np.ascontiguousarray(image)).pin_memory()
         rd = z.Reader(image=pinned, cache_size=0)
         C = int(rd.c_off[-1])
-        dev_out = torch.empty(total + 64, dtype=torch.uint8, device="cuda")
-        sampler = ClockSampler(local) if (name == "lz4" and rank == 0) else None
-        rd.load(0, rd.frames)                                       # compressed image resident in HBM
-        for _ in range(args.warmup):
+        dev_out = torch.zeros(total + 64, dtype=torch.uint8, device="cuda")
+        rd.load(0, rd.frames)
+        for _ in range(warmup):
             rd.decode_frames(0, rd.frames, dev_out)
+        dev_out.zero_()                                                       # the verified bytes are those of the timed passes
         barrier()
         l0 = rd.launch_count
         if sampler:
             sampler.mark_start()
         rd.timer_start()
-        wall0 = time.perf_counter()
         kernel_ms = 0.0
-        for _ in range(args.steps):
-            rd.decode_frames(0, rd.frames, dev_out)                 # inputs (C+D = 6 GB) >> L2, no flush needed
+        for _ in range(steps):
+            rd.decode_frames(0, rd.frames, dev_out)                           # inputs (C + D per step) >> L2: no flush needed
             kernel_ms += rd.last_decode_ms
-        kernel_name = rd.last_decode_kernel
         dev_ms = rd.timer_stop()
         barrier()
-        wall = time.perf_counter() - wall0
         if sampler:
             sampler.mark_end()
+        res = dict(total=total, C=C, frames=rd.frames, dev_ms=max_over_ranks(dev_ms), kernel_ms=max_over_ranks(kernel_ms),
+                   launches=rd.launch_count - l0, kernel=rd.last_decode_kernel,
+                   verified=int(min_over_ranks(verify_device(dev_out, total, period))))
+        return res, rd, pinned, dev_out
+
+    def e2e_leg(pinned, total, period, steps, scratch_dev):
+        """host image -> host buffer through zseek_b200_read_range; H2D + decode + D2H inside the timed region."""
+        rd2 = z.Reader(image=pinned, cache_size=0)
+        host_out = torch.zeros(total, dtype=torch.uint8).pin_memory()
+        for _ in range(2):
+            rd2.unload()
+            rd2.read_range_into(host_out, total, 0)
+        host_out.zero_()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            rd2.unload()
+            got = rd2.read_range_into(host_out, total, 0)
+            assert got == total
+        barrier()
+        t = max_over_ranks(time.perf_counter() - t0)
+        scratch_dev[:total].copy_(host_out, non_blocking=False)               # verify what arrived in the host buffer
+        ok = int(min_over_ranks(verify_device(scratch_dev, total, period)))
+        rd2.close()
+        del host_out
+        return t, ok
+
+    results, clocks = {}, None
+    # ---------------- configs[1] (headline) and configs[2]
+    for name, fname in (("lz4", "lz4.zsk"), ("zstd3", "zstd3.zsk")):
+        image = corpus.image(fname, corpus.reps)
+        sampler = ClockSampler(local) if (name == "lz4" and rank == 0) else None
+        res, rd, pinned, dev_out = decode_leg(image, corpus.total, tile, args.steps, args.warmup, sampler)
+        if sampler:
             clocks = sampler.stop()
-        launches = rd.launch_count - l0
-        dev_ms = max_over_ranks(dev_ms)
-        # spot-check the bytes that were just timed against the source tile (full parity lives in tests/)
-        chk = dev_out[:1 << 20].cpu().numpy()
-        results[name] = dict(total=total, C=C, dev_ms=dev_ms, kernel_ms=max_over_ranks(kernel_ms), wall=wall, launches=launches,
-                             frames=rd.frames, first_mib=chk, kernel=kernel_name)
-        launches_total += launches if name == "lz4" else 0
-        # ---- e2e: host buffers, H2D + decode + D2H inside the timed region (through zseek_b200_read_range)
-        if name == "lz4":
-            rd2 = z.Reader(image=pinned, cache_size=0)
-            host_out = torch.empty(total, dtype=torch.uint8).pin_memory()
-            for _ in range(2):
-                rd2.unload()
-                rd2.read_range_into(host_out, total, 0)
-            barrier()
-            t0 = time.perf_counter()
-            for _ in range(args.steps):
-                rd2.unload()
-                got = rd2.read_range_into(host_out, total, 0)
-                assert got == total
-            barrier()
-            e2e_t = max_over_ranks(time.perf_counter() - t0)
-            results[name]["e2e_s"] = e2e_t
-            results[name]["host_first_mib"] = host_out[:1 << 20].numpy().copy()
-            rd2.close()
-            del host_out
-        # ---- batched random 4 KiB preads over the zstd file (config 4 shape)
-        if name == "zstd3":
-            n_req = args.random_ops
-            offs = gen_offsets(n_req, total, 4096)
-            out = torch.empty(n_req * 4096, dtype=torch.uint8, device="cuda")
-            rdc = z.Reader(image=pinned, cache_size=rd.frames)       # decoded-frame cache can hold the file
-            rdc.load(0, rdc.frames)
-            rdc.pread_batch(offs, fixed_count=4096, dst=out, dst_stride=4096)  # untimed: one-time allocation of the batch buffers
-            rdc.cache_clear()
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            res = rdc.pread_batch(offs, fixed_count=4096, dst=out, dst_stride=4096)   # cold: decodes every touched frame
-            torch.cuda.synchronize()
-            cold = time.perf_counter() - t0
-            sample = out[:4096 * 64].cpu().numpy().copy()
-            warm = []
-            for _ in range(3):
-                t0 = time.perf_counter()
-                rdc.pread_batch(offs, fixed_count=4096, dst=out, dst_stride=4096)
-                torch.cuda.synchronize()
-                warm.append(time.perf_counter() - t0)
-            lat = []
-            for b in range(100):
-                rdc.cache_clear()
-                t0 = time.perf_counter()
-                rdc.pread_batch(gen_offsets(10000, total, 4096, seed=100 + b), fixed_count=4096, dst=out, dst_stride=4096)
-                torch.cuda.synchronize()
-                lat.append(time.perf_counter() - t0)
-            lat.sort()
-            results["random"] = dict(n=n_req, cold_s=cold, warm_s=min(warm), p50_ms=lat[len(lat) // 2] * 1e3,
-                                     p99_ms=lat[-1] * 1e3, short_reads=int((res < 4096).sum()), offs=offs,
-                                     sample=sample, res=res[:64].copy())
-            rdc.close()
-            del out
         rd.close()
-        del dev_out, pinned
+        res["e2e_s"], res["e2e_verified"] = e2e_leg(pinned, corpus.total, tile, args.steps, dev_out)
+        results[name] = res
+        log(f"[bench] {name}: {res['total'] * args.steps / res['dev_ms'] / 1e6:.1f} GB/s per GPU, e2e "
+            f"{res['total'] * args.steps / res['e2e_s'] / GB:.1f} GB/s, verified {res['verified']}/{res['total']} + {res['e2e_verified']}")
+        if name == "lz4" and world == 1 and corpus.tile > 512 * MIB:
+            # A/B: the same kernel on a 512 MiB tile x (size / 512 MiB) — replicas of a frame sit next to each other in the
+            # size-ordered job list and run in lock-step in one warp of the lane-per-frame kernel
+            from datagen import refwriter
+            payload, ent = refwriter.split(image.tobytes())
+            nfr = (512 * MIB) // 65536
+            small = payload[:int(ent[:nfr, 0].sum())] + refwriter.seek_table(ent[:nfr])
+            ab_img = np.frombuffer(refwriter.replicate(small, corpus.total // (512 * MIB)), dtype=np.uint8)
+            del payload
+            del dev_out, pinned
+            ab, rd_ab, p_ab, o_ab = decode_leg(ab_img, corpus.total, 512 * MIB, args.steps, 2)
+            rd_ab.close()
+            results["replica_ab"] = ab
+            del p_ab, o_ab, ab_img
+        else:
+            del dev_out, pinned
+        del image
+        torch.cuda.empty_cache()
+    pcie = pcie_ceiling() if rank == 0 else None
+
+    # ---------------- configs[4]: 1 MiB frames, LZ4 + zstd-19, 8 GiB per GPU, every rank its own shard
+    c5_total = int(args.c5_gib * (1 << 30))
+    for name, fname, period in (("lz4_1m", "lz4_1m.zsk", corpus.c5_lz4_tile), ("zstd19_1m", "zstd19_1m.zsk", corpus.c5_zstd_tile)):
+        if c5_total <= 0:
+            break
+        image = corpus.image(fname, max(1, c5_total // period))
+        res, rd, pinned, dev_out = decode_leg(image, (c5_total // period) * period if c5_total >= period else period, period, 3, 2)
+        rd.close()
+        results[name] = res
+        log(f"[bench] configs[4] {name}: {res['total'] * 3 / res['dev_ms'] / 1e6:.1f} GB/s per GPU, verified {res['verified']}/{res['total']}")
+        del dev_out, pinned, image
         torch.cuda.empty_cache()
 
-    # ---- CPU baseline (reference build) on rank 0, bounded sample
-    cpu = {}
-    if rank == 0:
-        from oracle.pyapi import RefReader
-        threads = os.cpu_count() or 1
-        for name in ("lz4", "zstd3"):
-            image, total = inputs[name]
-            sample = min(total, (1 << 30) if name == "lz4" else (1 << 30))
-            # sample = the first `sample` decompressed bytes of the same file
-            if world == 1:   # the CPU legs are timed at N = 1 only (other ranks would share the host cores)
-                t = cpu_scan(image, sample, threads)
-                t1 = cpu_scan(image, min(sample, 256 << 20), 1, repeats=1)
-                cpu[name] = dict(gbps=round(sample / t / GB, 3), gbps_1t=round(min(sample, 256 << 20) / t1 / GB, 3), threads=threads, sample=sample)
-            else:
-                cpu[name] = dict(gbps=None, gbps_1t=None, threads=0, sample=sample)
-            # correctness spot-check of what was timed on the GPU, against the reference reader
-            with RefReader(image) as rr:
-                want = np.frombuffer(rr.pread_full(1 << 20, 0), dtype=np.uint8)
-            assert (results[name]["first_mib"] == want).all(), f"{name}: GPU output differs from the reference"
-            if "host_first_mib" in results[name]:
-                assert (results[name]["host_first_mib"] == want).all(), f"{name}: e2e output differs from the reference"
-        image, total = inputs["zstd3"]
-        r = results["random"]
-        n_cpu = min(r["n"], 20000)
+    # ---------------- configs[3]: 1 M x 4 KiB random preads over a 16 GiB zstd-3 file (rank 0)
+    if rank == 0 and args.random_ops > 0:
+        rtotal = int(args.random_gib * (1 << 30))
+        rreps = max(1, rtotal // tile)
+        rtotal = rreps * tile
+        image = corpus.image("zstd3.zsk", rreps)
+        pinned = torch.from_numpy(np.ascontiguousarray(image)).pin_memory()
+        n_req = args.random_ops
+        offs = gen_offsets(n_req, rtotal, 4096)
+        out = torch.zeros(n_req * 4096, dtype=torch.uint8, device="cuda")
+        rdc = z.Reader(image=pinned, cache_size=1 << 30)                         # the decoded-frame cache can hold the file
+        d_off = np.asarray(rdc.d_off, dtype=np.uint64)
+        rdc.load(0, rdc.frames)
+        rdc.pread_batch(offs[:4096], fixed_count=4096, dst=out, dst_stride=4096)  # untimed: one-time allocation of the batch buffers
+        rdc.cache_clear()
+        out.zero_()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        res = rdc.pread_batch(offs, fixed_count=4096, dst=out, dst_stride=4096)   # cold: decodes every touched frame
+        torch.cuda.synchronize()
+        cold = time.perf_counter() - t0
+        # every request: length by B1 arithmetic, bytes against the writer's input (device gather)
+        ends = d_off[np.searchsorted(d_off, offs, side="right")]
+        want = np.minimum(np.uint64(4096), ends - offs).astype(np.int64)
+        len_ok = int((res == want).sum())
+        ar = torch.arange(4096, device="cuda", dtype=torch.int64)
+        bytes_ok, reqs_ok = 0, 0
+        for o in range(0, n_req, 8192):
+            k = min(8192, n_req - o)
+            so = torch.from_numpy(offs[o:o + k].astype(np.int64)).cuda()
+            ln = torch.from_numpy(want[o:o + k]).cuda()
+            exp = raw_dev[(so[:, None] + ar[None, :]) % tile]
+            got = out[o * 4096:(o + k) * 4096].view(k, 4096)
+            good = ((exp == got) | (ar[None, :] >= ln[:, None])).all(dim=1)
+            reqs_ok += int(good.sum())
+            bytes_ok += int(ln[good].sum())
+        warm = []
+        for _ in range(3):
+            t0 = time.perf_counter()
+            rdc.pread_batch(offs, fixed_count=4096, dst=out, dst_stride=4096)
+            torch.cuda.synchronize()
+            warm.append(time.perf_counter() - t0)
+        lat = []
+        for b in range(100):
+            rdc.cache_clear()
+            o10 = gen_offsets(10000, rtotal, 4096, seed=100 + b)
+            t0 = time.perf_counter()
+            rdc.pread_batch(o10, fixed_count=4096, dst=out, dst_stride=4096)
+            torch.cuda.synchronize()
+            lat.append(time.perf_counter() - t0)
+        lat.sort()
+        results["random"] = dict(n=n_req, total=rtotal, frames=rdc.frames, cold_s=cold, warm_s=min(warm), p50_ms=lat[len(lat) // 2] * 1e3,
+                                 p99_ms=lat[98] * 1e3, short_reads=int((res < 4096).sum()), lengths_ok=len_ok, requests_ok=reqs_ok,
+                                 verified_bytes=bytes_ok, expected_bytes=int(want.sum()), C=int(rdc.c_off[-1]))
+        rdc.close()
+        del out, pinned
+        torch.cuda.empty_cache()
+        log(f"[bench] random: cold {n_req / cold / 1e6:.2f} M ops/s, warm {n_req / min(warm) / 1e6:.1f} M ops/s, p50 {results['random']['p50_ms']:.2f} ms, "
+            f"{reqs_ok}/{n_req} requests verified")
+        # CPU figure for the same request list (bounded sample)
         if world == 1:
-            t, ops = cpu_random(image, r["offs"][:n_cpu], 4096, threads)
-            cpu["random"] = dict(ops=round(ops / t), threads=threads, n=n_cpu)
-        else:
-            cpu["random"] = dict(ops=None, threads=0, n=n_cpu)
-        with RefReader(image) as rr:
-            for i in range(64):
-                k, b = rr.pread(4096, int(r["offs"][i]))
-                assert k == r["res"][i] and r["sample"][i * 4096:i * 4096 + k].tobytes() == b, "random batch differs from reference"
+            from oracle.pyapi import RefDrive
+            threads = os.cpu_count() or 1
+            n_cpu = min(n_req, 20000)
+            t, ops = RefDrive.random(image, offs[:n_cpu], 4096, threads, cache_size=0, pin=True)
+            results["random"]["cpu"] = dict(ops=round(ops / t), threads=threads, n=n_cpu)
+        del image
+
+    # ---------------- CPU baseline (the reference build) on rank 0, N = 1 only (other ranks would share the host cores)
+    cpu = {}
+    if rank == 0 and world == 1:
+        threads = os.cpu_count() or 1
+        for name, fname in (("lz4", "lz4.zsk"), ("zstd3", "zstd3.zsk")):
+            image = corpus.image(fname, 1)
+            sample = min(corpus.tile, 1 << 30)
+            med, best = cpu_scan_stats(image, sample, threads)
+            med1, best1 = cpu_scan_stats(image, min(sample, 256 * MIB), 1, runs=3)
+            cpu[name] = dict(gbps=round(med, 3), best=round(best, 3), gbps_1t=round(med1, 3), threads=threads, sample=sample)
+            del image
 
     if rank == 0:
-        lz, zs, rn = results["lz4"], results["zstd3"], results["random"]
-        units = lz["total"] * world * args.steps
-        value = units / (lz["dev_ms"] / 1e3) / GB
-        alg = (lz["C"] + lz["total"]) * args.steps
-        achieved = alg / (lz["kernel_ms"] / 1e3) / GB
-        zs_value = zs["total"] * world * args.steps / (zs["dev_ms"] / 1e3) / GB
-        zs_ach = (zs["C"] + zs["total"]) * args.steps / (zs["kernel_ms"] / 1e3) / GB
+        lz, zs = results["lz4"], results["zstd3"]
+
+        def gbps(r, steps=args.steps, key="dev_ms"):
+            return r["total"] * world * steps / (r[key] / 1e3) / GB
+
+        def roof(r, steps=args.steps):
+            ach = (r["C"] + r["total"]) * steps / (r["kernel_ms"] / 1e3) / GB
+            return {"bound": "hbm", "achieved": round(ach, 1), "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 4),
+                    "traffic": profile_traffic(r["kernel"]), "kernel": r["kernel"], "algorithmic_bytes_per_launch": r["C"] + r["total"]}
+
+        config = workload_config(args)
+        config.update({"frames_per_gpu": lz["frames"], "compressed_bytes_per_gpu": lz["C"], "decompressed_bytes_per_gpu": lz["total"],
+                       "sharding": f"frame-range x{world}, no collective",
+                       "l2": "inputs (C+D per step) larger than L2; no flush needed", "timer": "CUDA events on the launching stream"})
+        extra = {
+            "zstd3_256k": {"workload": "BASELINE configs[2]: zstd level 3, 256 KiB frames, same size", "value": round(gbps(zs), 2), "unit": "GB/s",
+                           "ms_per_step": round(zs["dev_ms"] / args.steps, 3), "frames": zs["frames"], "compressed_bytes": zs["C"],
+                           "verified_bytes": zs["verified"], "roofline": roof(zs),
+                           "e2e": {"value": round(zs["total"] * world * args.steps / zs["e2e_s"] / GB, 2), "unit": "GB/s",
+                                   "verified_bytes": zs["e2e_verified"], "h2d_bytes_per_step": zs["C"], "d2h_bytes_per_step": zs["total"]},
+                           "cpu_baseline": ({"value": cpu["zstd3"]["gbps"], "best": cpu["zstd3"]["best"], "unit": "GB/s", "cores": cpu["zstd3"]["threads"],
+                                             "kind": "reference", "one_thread": cpu["zstd3"]["gbps_1t"]} if cpu else None)},
+            "kernel_ms_lz4_sum": round(lz["kernel_ms"], 3),
+        }
+        if pcie:
+            extra["pinned_copy_ceiling"] = {"h2d_GBps": round(pcie[0], 1), "d2h_GBps": round(pcie[1], 1),
+                                            "e2e_lz4_fraction_of_d2h": round(lz["total"] * args.steps / lz["e2e_s"] / GB / pcie[1], 3),
+                                            "note": "bare 1 GiB pinned copies on rank 0, same run; a host-buffer read cannot beat the D2H figure"}
+        if "replica_ab" in results:
+            ab = results["replica_ab"]
+            extra["replica_ab"] = {"tile_mib": 512, "value": round(gbps(ab), 2), "unit": "GB/s", "ms_per_step": round(ab["dev_ms"] / args.steps, 3),
+                                   "verified_bytes": ab["verified"], "note": "same kernel and size, file = 512 MiB tile replicated; the headline uses unique data"}
+        for k in ("lz4_1m", "zstd19_1m"):
+            if k in results:
+                r = results[k]
+                extra.setdefault("config5_1mib_frames", {})[k] = {
+                    "workload": f"BASELINE configs[4]: {k}, 1 MiB frames, {r['total'] / (1 << 30):g} GiB per GPU x {world} GPUs, frame-range shards",
+                    "value": round(gbps(r, 3), 2), "per_gpu": round(gbps(r, 3) / world, 2), "unit": "GB/s", "ms_per_step": round(r["dev_ms"] / 3, 3),
+                    "frames_per_gpu": r["frames"], "verified_bytes": r["verified"], "decompressed_bytes_per_gpu": r["total"], "roofline": roof(r, 3)}
+        if "random" in results:
+            rn = results["random"]
+            extra["random_4k"] = {
+                "workload": f"BASELINE configs[3]: {rn['n']} x 4 KiB zseek_pread requests, uniform byte offsets, over a {rn['total'] >> 30} GiB zstd-3 "
+                            f"file of {rn['frames']} frames (rank 0)",
+                "ops_per_s_cold": round(rn["n"] / rn["cold_s"]), "ops_per_s_warm_cache": round(rn["n"] / rn["warm_s"]),
+                "batch_10k_cold_p50_ms": round(rn["p50_ms"], 3), "batch_10k_cold_p99_ms": round(rn["p99_ms"], 3),
+                "short_reads_at_frame_boundaries": rn["short_reads"], "lengths_ok": rn["lengths_ok"], "requests_verified": rn["requests_ok"],
+                "verified_bytes": rn["verified_bytes"], "expected_bytes": rn["expected_bytes"],
+                "roofline_bound_ops_per_s": round(rn["n"] / ((rn["C"] + rn["total"] + 2 * rn["expected_bytes"]) / (peak * GB))),
+                "cpu_baseline": ({"value": rn["cpu"]["ops"], "unit": "ops/s", "cores": rn["cpu"]["threads"], "kind": "reference",
+                                  "sample": f"first {rn['cpu']['n']} requests"} if "cpu" in rn else None)}
         line = {
-            "metric": "decompressed_GBps", "value": round(value, 2), "unit": "GB/s", "n_gpus": world, "steps": args.steps,
+            "metric": "decompressed_GBps", "value": round(gbps(lz), 2), "unit": "GB/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(lz["dev_ms"] / args.steps, 3), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": f"BASELINE configs[1]: LZ4 level 0 seekable file, zsyn-v1, 64 KiB frames, "
-                                   f"{args.size_gib:g} GiB per GPU, full sequential decode",
-                       "frames_per_gpu": lz["frames"], "compressed_bytes_per_gpu": lz["C"], "decompressed_bytes_per_gpu": lz["total"],
-                       "tile_mib": args.tile_mib, "sharding": f"frame-range x{world}, no collective",
-                       "l2": "inputs (C+D per step) larger than L2; no flush needed", "timer": "CUDA events on the launching stream"},
-            "clocks": clocks,
+            "config": config, "clocks": clocks,
+            "verified_bytes": lz["verified"],
             "e2e": {"value": round(lz["total"] * world * args.steps / lz["e2e_s"] / GB, 2), "unit": "GB/s",
-                    "h2d_bytes_per_step": lz["C"], "d2h_bytes_per_step": lz["total"],
+                    "h2d_bytes_per_step": lz["C"], "d2h_bytes_per_step": lz["total"], "verified_bytes": lz["e2e_verified"],
                     "api": "zseek_b200_read_range, pinned host image -> pinned host buffer"},
-            "gpu_launches": launches_total,
-            "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-                         "frac": round(achieved / peak, 4), "traffic": profile_traffic(lz["kernel"]),
-                         "kernel": lz["kernel"], "algorithmic_bytes_per_launch": lz["C"] + lz["total"],
-                         "peak_source": peak_src},
-            "cpu_baseline": {"value": cpu["lz4"]["gbps"], "unit": "GB/s", "cores": cpu["lz4"]["threads"], "kind": "reference",
-                             "sample": (f"first {cpu['lz4']['sample'] >> 20} MiB of the same file, one reader per thread, 1 MiB zseek_pread "
-                                        f"requests, cache_size 0, best of 3; 1 thread: {cpu['lz4']['gbps_1t']} GB/s") if world == 1 else
-                                       "timed at N = 1 only; see the --impl reference line of this N"},
-            "extra": {
-                "zstd3_256k": {"workload": "BASELINE configs[2]: zstd level 3, 256 KiB frames", "value": round(zs_value, 2), "unit": "GB/s",
-                               "ms_per_step": round(zs["dev_ms"] / args.steps, 3), "frames": zs["frames"], "compressed_bytes": zs["C"],
-                               "roofline": {"bound": "hbm", "achieved": round(zs_ach, 1), "peak": peak, "frac": round(zs_ach / peak, 4),
-                                            "kernel": zs["kernel"], "traffic": profile_traffic(zs["kernel"])},
-                               "cpu_baseline": {"value": cpu["zstd3"]["gbps"], "unit": "GB/s", "cores": cpu["zstd3"]["threads"],
-                                                "kind": "reference", "one_thread": cpu["zstd3"]["gbps_1t"]}},
-                "random_4k": {"workload": f"BASELINE configs[3] shape: {rn['n']} x 4 KiB zseek_pread requests, uniform byte offsets, over the "
-                                          f"{zs['total'] >> 30} GiB zstd-3 file (rank 0)",
-                              "ops_per_s_cold": round(rn["n"] / rn["cold_s"]), "ops_per_s_warm_cache": round(rn["n"] / rn["warm_s"]),
-                              "batch_10k_cold_p50_ms": round(rn["p50_ms"], 3), "batch_10k_cold_p99_ms": round(rn["p99_ms"], 3),
-                              "short_reads_at_frame_boundaries": rn["short_reads"],
-                              "cpu_baseline": {"value": cpu["random"]["ops"], "unit": "ops/s", "cores": cpu["random"]["threads"],
-                                               "kind": "reference", "sample": f"first {cpu['random']['n']} requests"}},
-                "wall_s_lz4_timed_region": round(lz["wall"], 4), "kernel_ms_lz4_sum": round(lz["kernel_ms"], 3),
-            },
+            "gpu_launches": lz["launches"],
+            "roofline": dict(roof(lz), peak_source=peak_src),
+            "cpu_baseline": ({"value": cpu["lz4"]["gbps"], "best": cpu["lz4"]["best"], "unit": "GB/s", "cores": cpu["lz4"]["threads"], "kind": "reference",
+                              "sample": (f"first {cpu['lz4']['sample'] >> 20} MiB of the same file, one reader per thread, 1 MiB zseek_pread requests, "
+                                         f"cache_size 0, warm-up + 5 passes: value = median, best alongside; 1 thread: {cpu['lz4']['gbps_1t']} GB/s")}
+                             if cpu else {"value": None, "unit": "GB/s", "cores": 0, "kind": "reference",
+                                          "sample": "timed at N = 1 only; see the --impl reference line of this N"}),
+            "extra": extra,
         }
         emit(line)
     barrier()
-    cleanup_inputs(cache, rank)
 
 
 # ----------------------------------------------------------------------------- reference arm
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    inputs, cache = build_inputs(args, 0, 1)
-    image, total = inputs["lz4"]
+    corpus = Corpus(args)
+    corpus.build(need_all=False)
+    image = corpus.image("lz4.zsk", 1)
     threads = os.cpu_count() or 1
-    sample = min(total, 1 << 30)
+    sample = min(corpus.tile, 1 << 30)
     from oracle.pyapi import RefDrive
     for _ in range(args.warmup):
         RefDrive.scan(image, sample, threads, req=1 << 20, cache_size=0, pin=True)
@@ -420,18 +563,16 @@ def run_reference(args, rank, world):
         inner += t
     wall = time.perf_counter() - t0
     value = sample * args.steps / inner / GB
-    desc = (f"first {sample >> 20} MiB of the same {args.size_gib:g} GiB file per step, {threads} pinned threads, one reference reader "
+    desc = (f"each step = the first {sample >> 20} MiB of the same {args.size_gib:g} GiB file (a rate), {threads} pinned threads, one reference reader "
             f"per thread over a RAM image (memcpy pread), 1 MiB zseek_pread requests, cache_size 0")
     line = {"impl": "reference", "metric": "decompressed_GBps", "value": round(value, 3), "unit": "GB/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(inner / args.steps * 1e3, 3), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": f"BASELINE configs[1]: LZ4 level 0 seekable file, zsyn-v1, 64 KiB frames, {args.size_gib:g} GiB per GPU, "
-                                   f"full sequential decode", "tile_mib": args.tile_mib},
+            "config": workload_config(args),
             "cpu_baseline": {"value": round(value, 3), "unit": "GB/s", "cores": threads, "kind": "reference", "sample": desc},
             "e2e": {"value": round(value, 3), "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0, "extra": {"wall_s": round(wall, 3)}}
+            "gpu_launches": 0, "extra": {"wall_s": round(wall, 3), "sample": desc}}
     emit(line)
-    cleanup_inputs(cache, 0)
 
 
 _REAL_STDOUT = None
@@ -478,9 +619,13 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--size-gib", type=float, default=4.0)
-    ap.add_argument("--tile-mib", type=int, default=512)
+    ap.add_argument("--tile-mib", type=int, default=0, help="0 = unique data (tile = file size)")
     ap.add_argument("--random-ops", type=int, default=1000000)
+    ap.add_argument("--random-gib", type=float, default=16.0, help="size of the zstd-3 file of the random-read leg (configs[3]: 16)")
+    ap.add_argument("--c5-gib", type=float, default=8.0, help="per-GPU size of the configs[4] legs (0 = skip)")
     args = ap.parse_args()
+    if args.tile_mib <= 0:
+        args.tile_mib = int(args.size_gib * 1024)
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     claim_stdout()

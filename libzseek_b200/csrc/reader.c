@@ -103,7 +103,7 @@ struct zseek_reader {
     uint64_t *g_b_offsets, *g_b_counts, *g_b_dstoffs;
     int32_t *g_b_frame;
     uint32_t *g_b_inframe, *g_b_nbytes;
-    uint32_t *g_touched, *g_miss_ids, *g_miss_count;
+    uint32_t *g_touched;
     uint32_t *h_touched;
     uint8_t *g_out; /* device staging for host destinations */
     size_t g_out_cap;
@@ -369,6 +369,25 @@ static void cache_clear(zseek_reader_t *r)
     r->mir_lo = r->mir_hi = 0;
 }
 
+/* ------------------------------------------------------------------ pinned host buffers, allocated on first use */
+static bool ensure_stage(zseek_reader_t *r, char *errbuf)
+{
+    if (r->h_stage)
+        return true;
+    if (zsk_cuda_malloc_host(r->cx, (void **)&r->h_stage, 2 * r->stage_half))
+        return cuda_fail(r, errbuf, "allocate pinned staging");
+    return true;
+}
+
+static bool ensure_mirror(zseek_reader_t *r, char *errbuf)
+{
+    if (r->h_mirror)
+        return true;
+    if (zsk_cuda_malloc_host(r->cx, (void **)&r->h_mirror, 2 * r->mirror_cap))
+        return cuda_fail(r, errbuf, "allocate pinned window");
+    return true;
+}
+
 /* ------------------------------------------------------------------ compressed image residency */
 /* Queues the copy of file bytes [file_off, file_off + bytes) to device memory `dst` on the H2D
  * stream: one DMA straight from the memory image, or pread-callback -> pinned staging halves -> DMA. */
@@ -383,6 +402,8 @@ static bool h2d_range(zseek_reader_t *r, size_t file_off, size_t bytes, uint8_t 
             return cuda_fail(r, errbuf, "copy image to device");
         return true;
     }
+    if (!ensure_stage(r, errbuf))
+        return false;
     size_t done = 0;
     while (done < bytes) {
         size_t n = MIN(r->stage_half, bytes - done);
@@ -604,7 +625,7 @@ static void reader_free(zseek_reader_t *r)
         zsk_cuda_stream_sync(r->cx, ZSK_STREAM_D2H);
         void *dev[] = { r->g_coff, r->g_doff, r->g_comp, r->g_slab, r->g_frame_src, r->g_job_ids, r->g_job_offs, r->g_job_status, r->g_job_limits,
                         r->g_b_offsets, r->g_b_counts, r->g_b_dstoffs, r->g_b_frame, r->g_b_inframe, r->g_b_nbytes, r->g_touched,
-                        r->g_miss_ids, r->g_miss_count, r->g_out };
+                        r->g_out };
         for (size_t i = 0; i < sizeof(dev) / sizeof(dev[0]); i++)
             zsk_cuda_free(r->cx, dev[i]);
         void *pin[] = { r->h_stage, r->h_mirror, r->h_job_ids, r->h_job_offs, r->h_job_status, r->h_job_limits };
@@ -713,9 +734,9 @@ static zseek_reader_t *reader_open_common(zseek_reader_t *r, size_t cache_size, 
     if (zsk_cuda_malloc(r->cx, (void **)&r->g_coff, (N + 1) * sizeof(uint64_t)) ||
         zsk_cuda_malloc(r->cx, (void **)&r->g_doff, (N + 1) * sizeof(uint64_t)) ||
         zsk_cuda_malloc(r->cx, (void **)&r->g_frame_src, (N + 1) * sizeof(int64_t)) ||
-        zsk_cuda_malloc(r->cx, (void **)&r->g_slab, (size_t)r->nslots * r->slot_size + ZSK_PAD_FRONT + ZSK_PAD_BACK) ||
-        zsk_cuda_malloc_host(r->cx, (void **)&r->h_stage, r->mem_image ? 1 : 2 * r->stage_half) ||
-        zsk_cuda_malloc_host(r->cx, (void **)&r->h_mirror, 2 * r->mirror_cap)) {
+        zsk_cuda_malloc(r->cx, (void **)&r->g_slab, (size_t)r->nslots * r->slot_size + ZSK_PAD_FRONT + ZSK_PAD_BACK)) {
+        /* the pinned ingest staging (h_stage) and the pinned decoded window (h_mirror) are allocated on first use:
+         * readers that only serve device buffers or batches never pay for them */
         set_error(errbuf, "buffer creation failed: %s", zsk_cuda_error(r->cx));
         goto fail;
     }
@@ -807,7 +828,9 @@ static ssize_t pread_locked(zseek_reader_t *r, void *buf, size_t count, size_t o
             memcpy(buf, mirror_half(r, r->mir_cur) + (offset - r->d_off[r->mir_lo]), n);
             return (ssize_t)n;
         }
-        /* fall through: decode synchronously and report what fails */
+        /* fall through: some frame of the read-ahead window is bad; decode frame f alone and report only its verdict */
+        r->ra_window = 1;
+        r->ra_next = UINT64_MAX;
     }
     prefetch_drop(r);
     int32_t s = cache_find(r, f);
@@ -818,20 +841,37 @@ static ssize_t pread_locked(zseek_reader_t *r, void *buf, size_t count, size_t o
             r->ra_window = MIN(r->ra_window * 4, r->ra_max);
         else
             r->ra_window = 1;
+        if (!on_device && !ensure_mirror(r, errbuf))
+            return -1;
         uint64_t hi = MIN(f + (on_device ? MIN(r->ra_window, r->nslots) : r->ra_window), r->shard_hi);
+        bool ok;
         if (!on_device && hi - f > 1) {
             /* sequential host reader: decode the window through the H2D / decode / D2H pipeline straight into
              * the pinned mirror (one contiguous copy per chunk); later reads of the window are memcpys */
             r->mir_lo = r->mir_hi = 0;
-            if (!stream_frames_to_host(r, f, hi, mirror_half(r, r->mir_cur), call_data, errbuf))
+            ok = stream_frames_to_host(r, f, hi, mirror_half(r, r->mir_cur), call_data, errbuf);
+            if (ok) {
+                r->mir_lo = f;
+                r->mir_hi = hi;
+                r->ra_next = hi;
+                prefetch_start(r, call_data);
+            }
+        } else
+            ok = fill_window(r, f, hi, !on_device, call_data, errbuf);
+        if (!ok) {
+            /* the reference decodes only the frame a call asks for (src/decompress.c:700-790): a bad frame further
+             * ahead in the window must not fail this read.  Forget the window and decode frame f alone. */
+            if (hi - f <= 1)
                 return -1;
-            r->mir_lo = f;
-            r->mir_hi = hi;
+            r->ra_window = 1;
+            hi = f + 1;
+            if (!fill_window(r, f, hi, !on_device, call_data, errbuf)) {
+                r->ra_next = UINT64_MAX;
+                return -1;
+            }
+            r->ra_next = UINT64_MAX; /* the next call starts over with a window of one frame */
+        } else
             r->ra_next = hi;
-            prefetch_start(r, call_data);
-        } else if (!fill_window(r, f, hi, !on_device, call_data, errbuf))
-            return -1;
-        r->ra_next = hi;
         if (!on_device) {
             memcpy(buf, mirror_half(r, r->mir_cur) + (offset - r->d_off[r->mir_lo]), n);
             return (ssize_t)n;
@@ -889,7 +929,7 @@ bool zseek_reader_stats(zseek_reader_t *reader, zseek_reader_stats_t *stats, cha
     stats->decompressed_size = (size_t)reader->d_off[reader->nframes];
     stats->cache_memory = (size_t)reader->cached * reader->slot_size;
     stats->cached_frames = reader->cached;
-    stats->buffer_size = reader->g_comp_cap + (reader->mem_image ? 0 : 2 * reader->stage_half) + 2 * reader->mirror_cap;
+    stats->buffer_size = reader->g_comp_cap + (reader->h_stage ? 2 * reader->stage_half : 0) + (reader->h_mirror ? 2 * reader->mirror_cap : 0);
     pthread_mutex_unlock(&reader->lock);
     return true;
 }
@@ -1067,10 +1107,11 @@ static bool ensure_out(zseek_reader_t *r, size_t n, char *errbuf)
         return true;
     zsk_cuda_stream_sync(r->cx, ZSK_STREAM_COMPUTE);
     zsk_cuda_stream_sync(r->cx, ZSK_STREAM_D2H);
+    const size_t old_cap = r->g_out_cap;
     zsk_cuda_free(r->cx, r->g_out);
     r->g_out = NULL;
     r->g_out_cap = 0;
-    size_t want = MAX(n, 2 * r->g_out_cap);
+    size_t want = MAX(n, 2 * old_cap);
     if (zsk_cuda_malloc(r->cx, (void **)&r->g_out, want + ZSK_PAD_BACK)) {
         want = n;
         if (zsk_cuda_malloc(r->cx, (void **)&r->g_out, want + ZSK_PAD_BACK))
@@ -1315,9 +1356,7 @@ static bool ensure_batch(zseek_reader_t *r, size_t n, char *errbuf)
 {
     uint64_t N = r->nframes;
     if (!r->g_touched) {
-        if (zsk_cuda_malloc(r->cx, (void **)&r->g_touched, (N + 1) * sizeof(uint32_t)) ||
-            zsk_cuda_malloc(r->cx, (void **)&r->g_miss_ids, (N + 1) * sizeof(uint32_t)) ||
-            zsk_cuda_malloc(r->cx, (void **)&r->g_miss_count, sizeof(uint32_t)))
+        if (zsk_cuda_malloc(r->cx, (void **)&r->g_touched, (N + 1) * sizeof(uint32_t)))
             return cuda_fail(r, errbuf, "allocate batch buffers");
     }
     if (n <= r->batch_cap)
@@ -1371,17 +1410,9 @@ ssize_t zseek_b200_pread_batch(zseek_reader_t *r, size_t n, const uint64_t *offs
     int on_device = buf_on_device(r, dst);
     uint8_t *gdst = dst;
     size_t extent = 0;
+    uint32_t *nb = NULL; /* clipped byte count of every request (K1), host copy */
     if (!ensure_batch(r, n, errbuf))
         goto out;
-    if (!on_device) { /* host destination: gather into device staging, one D2H at the end */
-        for (size_t i = 0; i < n; i++) {
-            size_t e = (size_t)((dst_offs ? dst_offs[i] : i * dst_stride) + (counts ? counts[i] : fixed_count));
-            extent = MAX(extent, e);
-        }
-        if (!ensure_out(r, extent, errbuf))
-            goto out;
-        gdst = r->g_out;
-    }
     /* K1: lookup on the device */
     if (zsk_cuda_memcpy_async(r->cx, r->g_b_offsets, offsets, n * 8, ZSK_H2D, ZSK_STREAM_COMPUTE) ||
         (counts && zsk_cuda_memcpy_async(r->cx, r->g_b_counts, counts, n * 8, ZSK_H2D, ZSK_STREAM_COMPUTE)) ||
@@ -1392,11 +1423,35 @@ ssize_t zseek_b200_pread_batch(zseek_reader_t *r, size_t n, const uint64_t *offs
     }
     zsk_lookup_args la = { r->g_doff, (uint32_t)N, r->g_b_offsets, counts ? r->g_b_counts : NULL, fixed_count, (uint32_t)n,
                            r->g_b_frame, r->g_b_inframe, r->g_b_nbytes, r->g_touched };
+    const bool want_nb = results || !on_device;
+    if (want_nb && !(nb = malloc(n * sizeof(uint32_t)))) {
+        set_error(errbuf, "allocate results");
+        goto out;
+    }
     if (zsk_cuda_launch_lookup(r->cx, &la, ZSK_STREAM_COMPUTE) ||
         zsk_cuda_memcpy_async(r->cx, r->h_touched, r->g_touched, N * sizeof(uint32_t), ZSK_D2H, ZSK_STREAM_COMPUTE) ||
+        (want_nb && zsk_cuda_memcpy_async(r->cx, nb, r->g_b_nbytes, n * sizeof(uint32_t), ZSK_D2H, ZSK_STREAM_COMPUTE)) ||
         zsk_cuda_stream_sync(r->cx, ZSK_STREAM_COMPUTE)) {
         cuda_fail(r, errbuf, "lookup");
         goto out;
+    }
+    if (!on_device) {
+        /* host destination: gather into device staging laid out like the caller's buffer, then copy back ONLY the
+         * bytes the requests produced (the reference leaves everything else untouched: stride gaps, the tail of a
+         * read that ends at a frame boundary, requests at or after EOF) */
+        for (size_t i = 0; i < n; i++) {
+            if (!nb[i])
+                continue;
+            const uint64_t o = dst_offs ? dst_offs[i] : (uint64_t)i * dst_stride;
+            if (o + nb[i] < o || o + nb[i] > (uint64_t)SIZE_MAX / 2) {
+                set_error(errbuf, "batch destination out of range");
+                goto out;
+            }
+            extent = MAX(extent, (size_t)(o + nb[i]));
+        }
+        if (!ensure_out(r, extent, errbuf))
+            goto out;
+        gdst = r->g_out;
     }
     /* touched frames, ascending; processed in groups that fit the decoded-frame cache */
     zsk_gather_args ga = { r->g_b_frame, r->g_b_inframe, r->g_b_nbytes, r->g_frame_src, r->g_slab + ZSK_PAD_FRONT, gdst,
@@ -1436,31 +1491,36 @@ ssize_t zseek_b200_pread_batch(zseek_reader_t *r, size_t n, const uint64_t *offs
             goto out;
         }
     }
-    if (results) {
-        uint32_t *nb = malloc(n * sizeof(uint32_t));
-        if (!nb) {
-            set_error(errbuf, "allocate results");
-            goto out;
-        }
-        if (zsk_cuda_memcpy_async(r->cx, nb, r->g_b_nbytes, n * sizeof(uint32_t), ZSK_D2H, ZSK_STREAM_COMPUTE) ||
-            zsk_cuda_stream_sync(r->cx, ZSK_STREAM_COMPUTE)) {
-            free(nb);
-            cuda_fail(r, errbuf, "download results");
-            goto out;
-        }
+    if (results)
         for (size_t i = 0; i < n; i++)
             results[i] = nb[i];
-        free(nb);
-    }
     if (!on_device && extent) {
-        if (zsk_cuda_memcpy_async(r->cx, dst, gdst, extent, ZSK_D2H, ZSK_STREAM_COMPUTE) ||
-            zsk_cuda_stream_sync(r->cx, ZSK_STREAM_COMPUTE)) {
+        /* produced ranges, merged while they touch: full reads at a regular stride leave as one copy */
+        size_t run_lo = 0, run_hi = 0;
+        bool ok = true;
+        for (size_t i = 0; i <= n && ok; i++) {
+            const size_t o = i < n ? (size_t)(dst_offs ? dst_offs[i] : (uint64_t)i * dst_stride) : 0;
+            if (i < n && !nb[i])
+                continue;
+            if (i < n && run_hi > run_lo && o == run_hi) {
+                run_hi += nb[i];
+                continue;
+            }
+            if (run_hi > run_lo)
+                ok = !zsk_cuda_memcpy_async(r->cx, (uint8_t *)dst + run_lo, gdst + run_lo, run_hi - run_lo, ZSK_D2H, ZSK_STREAM_COMPUTE);
+            if (i < n) {
+                run_lo = o;
+                run_hi = o + nb[i];
+            }
+        }
+        if (!ok || zsk_cuda_stream_sync(r->cx, ZSK_STREAM_COMPUTE)) {
             cuda_fail(r, errbuf, "copy to host");
             goto out;
         }
     }
     ret = (ssize_t)n;
 out:
+    free(nb);
     pthread_mutex_unlock(&r->lock);
     return ret;
 }

@@ -15,9 +15,15 @@
 #ifdef ZSK_EMU
 #include "cuda_emu.h"
 #define ZSK_LDG(p) (*(p))
+#define ZSK_STCG(p, v) (*(p) = (v))
+#define ZSK_PREFETCH_L1(p) ((void)(p))
 #else
 #include <cuda_runtime.h>
 #define ZSK_LDG(p) __ldg(p)
+/* store that is kept out of L1 (scratch streams written once and read by a later kernel must not evict the lines the
+ * read streams of the same SM live in) */
+#define ZSK_STCG(p, v) __stcg((p), (v))
+#define ZSK_PREFETCH_L1(p) asm volatile("prefetch.global.L1 [%0];" ::"l"(p))
 #endif
 
 #define ZSK_FULL 0xffffffffu

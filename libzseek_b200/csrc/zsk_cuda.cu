@@ -12,7 +12,6 @@
 #include "zsk_cuda.h"
 #include "zsk_lz4.cuh"
 #include "zsk_lz4_lane.cuh"
-#include "zsk_lz4_lane2.cuh"
 #include "zsk_zstd_pipe.cuh"
 #include "zsk_seek.cuh"
 
@@ -37,7 +36,7 @@ struct zsk_cuda_ctx {
     uint32_t *zdeferred;
     size_t zjobs_cap;
     zsk_zblock *zblocks;
-    uint64_t *zseqs;
+    uint32_t *zseqs;
     uint8_t *zlits;
     size_t zblocks_cap, zseqs_cap, zlits_cap;
     unsigned long long *zctr;            /* ZSK_NCOUNTERS blocks of ZSK_ZC_N counters */
@@ -45,9 +44,7 @@ struct zsk_cuda_ctx {
     int zfse_ctas, zhuf_ctas, zexec_ctas;
     uint64_t zwave_bytes;                /* ZSEEK_B200_ZSTD_WAVE_MB (default 4096) */
     int zstd_legacy;                     /* ZSEEK_B200_ZSTD_LEGACY=1: every frame goes to the one-CTA-per-frame kernel (A/B runs) */
-    int lz4_group;                       /* lanes per LZ4 frame (ZSEEK_B200_LZ4_GROUP: 4, 8, 16 or 32) */
     int lz4_lane_ctas;                   /* resident CTAs of the lane-per-frame kernel */
-    int lz4_lane2, lz4_lane2_ctas;       /* ZSEEK_B200_LZ4_LANE2=1: the two-micro-ops-per-trip variant */
     unsigned lz4_lane_min;               /* launches with at least this many frames use the lane-per-frame kernel */
     unsigned long long launches;
     int trace;                           /* ZSEEK_B200_TRACE=1: timeline of the host-destination pipeline */
@@ -148,15 +145,7 @@ int zsk_cuda_ctx_create(int device, zsk_cuda_ctx **out, char *err, size_t errlen
     }
     cx->zexec_ctas = (per_sm < 1 ? 1 : per_sm) * cx->sm_count;
     CK0(cudaMalloc((void **)&cx->zctr, ZSK_NCOUNTERS * ZSK_ZC_N * sizeof(unsigned long long)));
-    cx->lz4_group = 401;                 /* 401 = batch kernel (warp per frame, default); 1 = lock-step kernel (8 lanes per frame) */
-    if (const char *g = getenv("ZSEEK_B200_LZ4_GROUP")) {
-        int v = atoi(g);
-        if (v == 4 || v == 8 || v == 16 || v == 32) cx->lz4_group = v;   /* plain per-group variants, for A/B runs */
-        if (v == 104 || v == 116) cx->lz4_group = v;                     /* lock-step variants with 4 / 16 lanes per frame */
-        if (v == 401 || v == 1) cx->lz4_group = v;
-    }
-    if (cx->lz4_group == 401) CK0(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, zsk_lz4_decode_batch_kernel, ZSK_LZ4_CTA_THREADS, 0));
-    else CK0(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, zsk_lz4_decode_lockstep_kernel<8>, ZSK_LZ4_CTA_THREADS, 0));
+    CK0(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, zsk_lz4_decode_batch_kernel, ZSK_LZ4_CTA_THREADS, 0));
     if (per_sm < 1) per_sm = 1;
     if (const char *g = getenv("ZSEEK_B200_LZ4_CTAS_PER_SM")) { /* tuning knob: resident LZ4 CTAs per SM */
         int v = atoi(g);
@@ -174,16 +163,6 @@ int zsk_cuda_ctx_create(int device, zsk_cuda_ctx **out, char *err, size_t errlen
         if (v >= 1 && v < per_sm) per_sm = v;
     }
     cx->lz4_lane_ctas = per_sm * cx->sm_count;
-    CK0(cudaFuncSetAttribute(zsk_lz4_decode_lane2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ZSK_LZ4L2_SMEM));
-    CK0(cudaFuncSetAttribute(zsk_lz4_decode_lane2_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    CK0(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, zsk_lz4_decode_lane2_kernel, ZSK_LZ4L_THREADS, ZSK_LZ4L2_SMEM));
-    if (per_sm < 1) per_sm = 1;
-    if (const char *g = getenv("ZSEEK_B200_LZ4_LANE_CTAS_PER_SM")) {
-        int v = atoi(g);
-        if (v >= 1 && v < per_sm) per_sm = v;
-    }
-    cx->lz4_lane2_ctas = per_sm * cx->sm_count;
-    if (const char *g = getenv("ZSEEK_B200_LZ4_LANE2")) cx->lz4_lane2 = atoi(g);
     cx->lz4_lane_min = 40960;             /* measured crossover: 32,768 frames 11.6 ms (warp per frame) vs 14.1 ms (lane per frame), 49,152 frames 18.6 vs 15.9 ms */
     if (const char *g = getenv("ZSEEK_B200_LZ4_LANE_MIN")) cx->lz4_lane_min = (unsigned)strtoul(g, NULL, 10); /* 0 = always, huge = never */
     if (const char *g = getenv("ZSEEK_B200_TRACE")) cx->trace = atoi(g);
@@ -377,17 +356,17 @@ static int launch_zstd_pipeline(zsk_cuda_ctx *cx, zsk_decode_args a, cudaStream_
         if ((rc = grow_pool(cx, (void **)&cx->zdeferred, &cap_d, njobs * sizeof(uint32_t)))) return rc;
         cx->zjobs_cap = cap_f / sizeof(zsk_zframe) < cap_d / sizeof(uint32_t) ? cap_f / sizeof(zsk_zframe) : cap_d / sizeof(uint32_t);
     }
-    /* pool sizes for typical data: one block per 2 KiB of output, one sequence per 4 bytes, 3/4 of the output as
+    /* pool sizes for typical data: one block per 2 KiB of output, one sequence (12 bytes of records) per 5 bytes, 3/4 of the output as
      * Huffman literals; frames beyond that are deferred to the old kernel by P0 */
     const size_t want_blocks = (size_t)(dsum / 2048) + 4 * njobs + 64;
-    const size_t want_seqs = (size_t)(dsum / 4) + 64 * njobs + 1024;
+    const size_t want_seqs = (size_t)(dsum / 5) + 64 * njobs + 1024;
     const size_t want_lits = (size_t)(dsum / 4 * 3) + 64 * njobs + 4096;
-    size_t cap_b = cx->zblocks_cap * sizeof(zsk_zblock), cap_s = cx->zseqs_cap * sizeof(uint64_t), cap_l = cx->zlits_cap ? cx->zlits_cap + ZSK_PAD_BACK : 0;
+    size_t cap_b = cx->zblocks_cap * sizeof(zsk_zblock), cap_s = cx->zseqs_cap * 3 * sizeof(uint32_t), cap_l = cx->zlits_cap ? cx->zlits_cap + ZSK_PAD_BACK : 0;
     if ((rc = grow_pool(cx, (void **)&cx->zblocks, &cap_b, want_blocks * sizeof(zsk_zblock)))) return rc;
-    if ((rc = grow_pool(cx, (void **)&cx->zseqs, &cap_s, want_seqs * sizeof(uint64_t)))) return rc;
+    if ((rc = grow_pool(cx, (void **)&cx->zseqs, &cap_s, want_seqs * 3 * sizeof(uint32_t)))) return rc;
     if ((rc = grow_pool(cx, (void **)&cx->zlits, &cap_l, want_lits + ZSK_PAD_BACK))) return rc;
     cx->zblocks_cap = cap_b / sizeof(zsk_zblock);
-    cx->zseqs_cap = cap_s / sizeof(uint64_t);
+    cx->zseqs_cap = cap_s / (3 * sizeof(uint32_t));
     cx->zlits_cap = cap_l - ZSK_PAD_BACK;
 
     zsk_zpipe_args z;
@@ -425,33 +404,17 @@ int zsk_cuda_launch_decode(zsk_cuda_ctx *cx, int codec, const zsk_decode_args *a
     a.job_list_count = NULL;
     cudaStream_t s = cx->streams[stream];
     CK(cx, cudaEventRecord(cx->k0, s));
-    if (codec == ZSK_CODEC_LZ4 && cx->lz4_group == 401 && a.njobs >= cx->lz4_lane_min) {
+    if (codec == ZSK_CODEC_LZ4 && a.njobs >= cx->lz4_lane_min) {
         unsigned ctas = (a.njobs + ZSK_LZ4L_THREADS - 1) / ZSK_LZ4L_THREADS;
-        if (cx->lz4_lane2) {
-            if (ctas > (unsigned)cx->lz4_lane2_ctas) ctas = (unsigned)cx->lz4_lane2_ctas;
-            zsk_lz4_decode_lane2_kernel<<<ctas, ZSK_LZ4L_THREADS, ZSK_LZ4L2_SMEM, s>>>(a);
-            cx->k_name = "zsk_lz4_decode_lane2_kernel";
-        } else {
-            if (ctas > (unsigned)cx->lz4_lane_ctas) ctas = (unsigned)cx->lz4_lane_ctas;
-            zsk_lz4_decode_lane_kernel<<<ctas, ZSK_LZ4L_THREADS, ZSK_LZ4L_SMEM, s>>>(a);
-            cx->k_name = "zsk_lz4_decode_lane_kernel";
-        }
+        if (ctas > (unsigned)cx->lz4_lane_ctas) ctas = (unsigned)cx->lz4_lane_ctas;
+        zsk_lz4_decode_lane_kernel<<<ctas, ZSK_LZ4L_THREADS, ZSK_LZ4L_SMEM, s>>>(a);
+        cx->k_name = "zsk_lz4_decode_lane_kernel";
     } else if (codec == ZSK_CODEC_LZ4) {
-        unsigned frames_per_cta = ZSK_LZ4_CTA_THREADS / (unsigned)(cx->lz4_group > 1 ? cx->lz4_group % 100 : 8);
-        if (cx->lz4_group == 401) frames_per_cta = ZSK_LZ4_CTA_THREADS / 32;
+        const unsigned frames_per_cta = ZSK_LZ4_CTA_THREADS / 32;
         unsigned ctas = (a.njobs + frames_per_cta - 1) / frames_per_cta;
         if (ctas > (unsigned)cx->lz4_ctas) ctas = (unsigned)cx->lz4_ctas;
-        cx->k_name = cx->lz4_group == 401 ? "zsk_lz4_decode_batch_kernel" : cx->lz4_group < 100 && cx->lz4_group > 1 ? "zsk_lz4_decode_kernel" : "zsk_lz4_decode_lockstep_kernel";
-        switch (cx->lz4_group) {
-        case 4: zsk_lz4_decode_kernel<4><<<ctas, ZSK_LZ4_CTA_THREADS, 0, s>>>(a); break;
-        case 16: zsk_lz4_decode_kernel<16><<<ctas, ZSK_LZ4_CTA_THREADS, 0, s>>>(a); break;
-        case 32: zsk_lz4_decode_kernel<32><<<ctas, ZSK_LZ4_CTA_THREADS, 0, s>>>(a); break;
-        case 8: zsk_lz4_decode_kernel<8><<<ctas, ZSK_LZ4_CTA_THREADS, 0, s>>>(a); break;
-        case 401: zsk_lz4_decode_batch_kernel<<<ctas, ZSK_LZ4_CTA_THREADS, 0, s>>>(a); break;
-        case 104: zsk_lz4_decode_lockstep_kernel<4><<<ctas, ZSK_LZ4_CTA_THREADS, 0, s>>>(a); break;
-        case 116: zsk_lz4_decode_lockstep_kernel<16><<<ctas, ZSK_LZ4_CTA_THREADS, 0, s>>>(a); break;
-        default: zsk_lz4_decode_lockstep_kernel<8><<<ctas, ZSK_LZ4_CTA_THREADS, 0, s>>>(a); break;
-        }
+        zsk_lz4_decode_batch_kernel<<<ctas, ZSK_LZ4_CTA_THREADS, 0, s>>>(a);
+        cx->k_name = "zsk_lz4_decode_batch_kernel";
     } else if (codec == ZSK_CODEC_ZSTD && cx->zstd_legacy) {
         if (!cx->scratch) CK(cx, cudaMalloc((void **)&cx->scratch, (size_t)cx->zstd_ctas * ZSK_LIT_SCRATCH + ZSK_PAD_BACK));
         a.scratch = cx->scratch;

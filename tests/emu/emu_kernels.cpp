@@ -5,7 +5,6 @@
 #include "cuda_emu.h"
 #include "../../libzseek_b200/csrc/zsk_lz4.cuh"
 #include "../../libzseek_b200/csrc/zsk_lz4_lane.cuh"
-#include "../../libzseek_b200/csrc/zsk_lz4_lane2.cuh"
 #include "../../libzseek_b200/csrc/zsk_zstd_pipe.cuh"
 #include "../../libzseek_b200/csrc/zsk_seek.cuh"
 
@@ -28,7 +27,7 @@ static void emu_zstd_pipeline(zsk_decode_args a, uint32_t njobs, uint32_t ctas, 
     z.lits_cap = tiny_pools ? 20000 : dsum / 4 * 3 + 64 * njobs + 4096;
     std::vector<zsk_zframe> frames(njobs + 1);
     std::vector<zsk_zblock> blocks(z.blocks_cap + 1);
-    std::vector<uint64_t> seqs(z.seqs_cap + 1, 0xEEEEEEEEEEEEEEEEull);
+    std::vector<uint32_t> seqs(3 * z.seqs_cap + 3, 0xEEEEEEEEu);
     std::vector<uint8_t> lits(z.lits_cap + ZSK_PAD_BACK, 0xEE);
     std::vector<uint32_t> deferred(njobs + 1);
     unsigned long long ctr[ZSK_ZC_N] = { 0 };
@@ -65,8 +64,6 @@ void emu_decode(int codec, const uint8_t *comp, uint64_t comp_base, const uint64
     a.status = status; a.work_counter = &counter; a.scratch = scratch.data(); a.limits = limits;
     a.dsize_sum = 0; a.job_list = nullptr; a.job_list_count = nullptr;
     if (codec == 1) emu::launch(dim3(ctas), dim3(ZSK_LZ4_CTA_THREADS), 0, [&] { zsk_lz4_decode_batch_kernel(a); });           /* shipped default */
-    else if (codec == 101) emu::launch(dim3(ctas), dim3(ZSK_LZ4_CTA_THREADS), 0, [&] { zsk_lz4_decode_lockstep_kernel<8>(a); }); /* alternative */
-    else if (codec == 103) emu::launch(dim3(ctas), dim3(ZSK_LZ4L_THREADS), ZSK_LZ4L2_SMEM, [&] { zsk_lz4_decode_lane2_kernel(a); }); /* two micro-ops per trip */
     else if (codec == 102) emu::launch(dim3(ctas), dim3(ZSK_LZ4L_THREADS), ZSK_LZ4L_SMEM, [&] { zsk_lz4_decode_lane_kernel(a); });  /* many-frame launches */
     else if (codec == 200) emu::launch(dim3(ctas), dim3(ZSK_ZSTD_CTA_THREADS), 0, [&] { zsk_zstd_decode_kernel(a); }); /* one CTA per frame: only deferred frames in the product */
     else emu_zstd_pipeline(a, njobs, ctas, d_off, first_frame, frame_ids, codec == 201);

@@ -59,21 +59,10 @@ def test_emulated_zstd_pipeline_unaligned_output(emu, golden, name, misalign):
     assert hashlib.sha256(out.tobytes()).hexdigest() == c["input_sha256"]
 
 
-@pytest.mark.parametrize("name", ["zsyn_lz4_64k", "zsyn_lz4_256k_linked", "mix_lz4"])
-def test_emulated_lockstep_lz4_kernel(emu, golden, name):
-    """The alternative LZ4 kernel (8-lane groups in lock-step, ZSEEK_B200_LZ4_GROUP=1) stays correct too."""
-    cases, _ = golden
-    c = cases[name]
-    with OraclePort(c["image"]) as op:
-        out, status = emu_api.decode_all(emu, c["image"], 101, op.c_off, op.d_off, ctas=2)
-    assert (status == 0).all(), status
-    assert hashlib.sha256(out.tobytes()).hexdigest() == c["input_sha256"]
-
-
 LZ4_CASES = ["tiny_lz4", "zsyn_lz4_64k", "zsyn_lz4_256k_linked", "mix_lz4"]
 
 
-LANE_KERNELS = [102, 103]   # one micro-op per trip (shipped for many-frame launches) / two micro-ops per trip
+LANE_KERNELS = [102]   # the lane-per-frame kernel (launches with many frames)
 
 
 @pytest.mark.parametrize("kernel", LANE_KERNELS)
@@ -100,7 +89,7 @@ def test_emulated_lane_lz4_kernel_unaligned_output(emu, golden, misalign, kernel
     assert hashlib.sha256(out.tobytes()).hexdigest() == c["input_sha256"]
 
 
-@pytest.mark.parametrize("name,codec", [("zsyn_lz4_64k", None), ("zsyn_lz4_64k", 102), ("zsyn_lz4_64k", 103), ("zsyn_zstd3_128k", None),
+@pytest.mark.parametrize("name,codec", [("zsyn_lz4_64k", None), ("zsyn_lz4_64k", 102), ("zsyn_zstd3_128k", None),
                                         ("zsyn_zstd3_128k", 200), ("zsyn_zstd3_128k", 201)])
 def test_emulated_decode_flags_corrupt_frames(emu, golden, name, codec):
     """Truncation and bit flips must end in a non-zero status, never a hang or an out-of-bounds write."""
@@ -185,14 +174,13 @@ def test_emulated_lane_lz4_kernel_sequence_shapes(emu, kw):
     image = foreign.build(data, 100000, "lz4", **kw)
     with OraclePort(image) as op:
         assert op.decode_all().tobytes() == data
-        for codec, mis in ((102, 0), (102, 3), (103, 0), (103, 5), (1, 0)):
+        for codec, mis in ((102, 0), (102, 3), (1, 0), (1, 5)):
             out, status = emu_api.decode_all(emu, image, codec, op.c_off, op.d_off, ctas=1, misalign=mis)
             assert (status == 0).all(), status
             assert out.tobytes() == data
 
 
 @pytest.mark.parametrize("name,codec", [("zsyn_lz4_64k", 1), ("zsyn_lz4_64k", 102), ("zsyn_lz4_256k_linked", 102), ("mix_lz4", 1),
-                                        ("zsyn_lz4_64k", 103), ("mix_lz4", 103),
                                         ("zsyn_zstd3_128k", None), ("zsyn_zstd19_256k", None), ("mix_zstd3", None),
                                         ("zsyn_zstd3_128k", 200), ("mix_zstd3", 201)])
 def test_emulated_decode_stops_at_job_limits(emu, golden, name, codec):
@@ -234,7 +222,7 @@ def test_emulated_kernels_verify_checksums_like_the_reference(emu):
     for name, data, good in _checksum_cases():
         with OraclePort(good) as op:
             c_off, d_off, codec = op.c_off.copy(), op.d_off.copy(), op.codec
-        kernels = (1, 102, 103) if name.startswith("lz4") else (codec,)
+        kernels = (1, 102) if name.startswith("lz4") else (codec,)
         c0, c1, c2 = int(c_off[0]), int(c_off[1]), int(c_off[2])
         flips = {"intact": None, "content checksum of frame 0": c1 - 1, "payload of frame 1": c1 + (c2 - c1) // 2,
                  "frame header of frame 1": c1 + 5}
@@ -291,7 +279,7 @@ def test_emulated_lz4_kernels_on_random_mixtures(emu, seed):
     image = refwriter.write(data, LZ4, int(rng.choice([0, 3, 9])), frame, int(rng.choice([frame, 4093])))
     with OraclePort(image) as op:
         assert op.decode_all().tobytes() == data
-        for codec, mis in ((1, 0), (102, 0), (102, 13), (103, 7)):
+        for codec, mis in ((1, 0), (102, 0), (102, 13), (1, 7)):
             out, status = emu_api.decode_all(emu, image, codec, op.c_off, op.d_off, ctas=1, misalign=mis)
             assert (status == 0).all(), (codec, status)
             assert out.tobytes() == data, codec
