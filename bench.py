@@ -389,6 +389,63 @@ def run_b200(args, rank, world):
         del dev_out, pinned, image
         torch.cuda.empty_cache()
 
+    # ---------------- x1: gather of the decoded shards to rank 0 over NVLink (N > 1): the 4 GiB LZ4 file sharded by frame range
+    if world > 1:
+        from libzseek_b200.sharding import decode_and_gather, gather_to, shard_range
+        image = corpus.image("lz4.zsk", corpus.reps)
+        pinned = torch.from_numpy(np.ascontiguousarray(image)).pin_memory()
+        rd = z.Reader(image=pinned, cache_size=0)
+        rd.set_shard(rank, world)
+        lo, hi = shard_range(rd.frames, rank, world)
+        d_off = rd.d_off
+        nbytes = int(d_off[hi] - d_off[lo])
+        rd.load(lo, hi)
+        whole = torch.zeros(corpus.total + 64, dtype=torch.uint8, device="cuda") if rank == 0 else None
+        local_buf = torch.zeros(nbytes + 64, dtype=torch.uint8, device="cuda")
+        chunk = 128 * MIB
+
+        def decode_chunk(f0, f1, view):
+            rd.decode_frames(f0, f1, view)
+
+        def timed(fn, reps=3):
+            fn()
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                fn()
+            e1.record()
+            e1.synchronize()
+            barrier()
+            return max_over_ranks(e0.elapsed_time(e1) / reps)
+
+        from libzseek_b200.sharding import chunk_plan
+        plan = chunk_plan(d_off, lo, hi, chunk)
+        base = int(d_off[lo])
+
+        def decode_only():
+            for f0, f1 in plan:
+                decode_chunk(f0, f1, local_buf[int(d_off[f0]) - base:int(d_off[f1]) - base])
+
+        def gather_only():
+            gather_to(local_buf[:nbytes], d_off, dst_rank=0, out=whole)
+
+        def pipeline():
+            decode_and_gather(decode_chunk, d_off, out=whole, local=local_buf, dst_rank=0, chunk_bytes=chunk)
+
+        t_dec, t_gat, t_pipe = timed(decode_only), timed(gather_only), timed(pipeline)
+        if rank == 0:
+            whole.zero_()
+        pipeline()
+        torch.cuda.synchronize()
+        barrier()
+        ok = verify_device(whole, corpus.total, tile) if rank == 0 else 0
+        moved = corpus.total - (int(d_off[shard_range(rd.frames, 0, world)[1]]) - int(d_off[shard_range(rd.frames, 0, world)[0]]))
+        results["gather"] = dict(decode_ms=t_dec, gather_ms=t_gat, pipeline_ms=t_pipe, moved=moved, verified=ok, total=corpus.total)
+        rd.close()
+        del whole, local_buf, pinned, image
+        torch.cuda.empty_cache()
+
     # ---------------- configs[3]: 1 M x 4 KiB random preads over a 16 GiB zstd-3 file (rank 0)
     if rank == 0 and args.random_ops > 0:
         rtotal = int(args.random_gib * (1 << 30))
@@ -509,6 +566,14 @@ def run_b200(args, rank, world):
                     "workload": f"BASELINE configs[4]: {k}, 1 MiB frames, {r['total'] / (1 << 30):g} GiB per GPU x {world} GPUs, frame-range shards",
                     "value": round(gbps(r, 3), 2), "per_gpu": round(gbps(r, 3) / world, 2), "unit": "GB/s", "ms_per_step": round(r["dev_ms"] / 3, 3),
                     "frames_per_gpu": r["frames"], "verified_bytes": r["verified"], "decompressed_bytes_per_gpu": r["total"], "roofline": roof(r, 3)}
+        if "gather" in results:
+            g = results["gather"]
+            extra["gather_to_rank0"] = {
+                "workload": f"the {g['total'] >> 30} GiB LZ4 file sharded by frame range over {world} GPUs, decoded shards collected on rank 0 (NCCL send/recv over NVLink)",
+                "gather_GBps_into_rank0": round(g["moved"] / (g["gather_ms"] / 1e3) / GB, 1), "gather_ms": round(g["gather_ms"], 3),
+                "decode_ms": round(g["decode_ms"], 3), "decode_then_send_pipeline_ms": round(g["pipeline_ms"], 3),
+                "fraction_of_gather_hidden_behind_decode": round(max(0.0, min(1.0, (g["decode_ms"] + g["gather_ms"] - g["pipeline_ms"]) / g["gather_ms"])), 3),
+                "verified_bytes": g["verified"], "chunk_mib": 128, "timer": "CUDA events on the current stream, max over ranks"}
         if "random" in results:
             rn = results["random"]
             extra["random_4k"] = {

@@ -26,6 +26,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <sys/stat.h>
+#include <unistd.h>
 
 #include "../../include/zseek_b200.h"
 #include "zsk_cuda.h"
@@ -42,6 +43,11 @@ struct zseek_reader {
     int codec;
     pthread_mutex_t lock;
     size_t pos;
+
+    /* default FILE* I/O (zseek_reader_open): the descriptor behind the FILE*, read with pread(2) from a small worker pool
+     * when a large range is pulled into the pinned staging; -1 = caller-supplied callbacks */
+    int file_fd;
+    struct io_pool *io;
 
     /* memory-image mode (zseek_b200_reader_open_mem) */
     const uint8_t *mem_image;
@@ -131,6 +137,7 @@ static bool stream_frames_finish(zseek_reader_t *r, uint64_t lo, uint64_t hi, bo
 static void prefetch_drop(zseek_reader_t *r);
 static void prefetch_start(zseek_reader_t *r, void *call_data);
 static uint8_t *mirror_half(zseek_reader_t *r, int which);
+static size_t env_size(const char *name, size_t dflt);
 
 static void set_error(char errbuf[ZSEEK_ERRBUF_SIZE], const char *fmt, ...)
 {
@@ -369,6 +376,116 @@ static void cache_clear(zseek_reader_t *r)
     r->mir_lo = r->mir_hi = 0;
 }
 
+/* ------------------------------------------------------------------ parallel file ingest (default FILE* I/O only) */
+/* The callback interface (reference src/zseek.h:88-116) hands the library one buffer per call, and the default callbacks
+ * (reference src/decompress.c:47-98) seek a shared FILE*: one thread at a time.  When the reader was opened over a FILE*,
+ * the library knows the descriptor and may read it with pread(2), which needs no file position: a few worker threads
+ * fill one staging half in parallel (page cache -> pinned memory runs at memcpy speed per thread), the caller's thread
+ * queues the DMA of the half that is complete. */
+typedef struct io_pool {
+    pthread_t th[16];
+    int n;
+    pthread_mutex_t mu;
+    pthread_cond_t cv_work, cv_done;
+    int fd;
+    uint8_t *dst;
+    size_t off, len, piece, next;
+    int pending, err;
+    bool stop;
+} io_pool;
+
+static void *io_worker(void *arg)
+{
+    io_pool *p = arg;
+    pthread_mutex_lock(&p->mu);
+    for (;;) {
+        while (!p->stop && p->next >= p->len)
+            pthread_cond_wait(&p->cv_work, &p->mu);
+        if (p->stop)
+            break;
+        const size_t o = p->next, n = MIN(p->piece, p->len - o);
+        p->next += n;
+        const int fd = p->fd;
+        uint8_t *dst = p->dst + o;
+        const size_t foff = p->off + o;
+        pthread_mutex_unlock(&p->mu);
+        size_t done = 0;
+        int err = 0;
+        while (done < n) {
+            ssize_t k = pread(fd, dst + done, n - done, (off_t)(foff + done));
+            if (k < 0 && errno == EINTR)
+                continue;
+            if (k <= 0) {
+                err = k < 0 ? 1 : 2; /* 2: unexpected EOF */
+                break;
+            }
+            done += (size_t)k;
+        }
+        pthread_mutex_lock(&p->mu);
+        if (err && !p->err)
+            p->err = err;
+        if (--p->pending == 0)
+            pthread_cond_signal(&p->cv_done);
+    }
+    pthread_mutex_unlock(&p->mu);
+    return NULL;
+}
+
+static io_pool *io_pool_create(int threads)
+{
+    io_pool *p = calloc(1, sizeof(*p));
+    if (!p)
+        return NULL;
+    pthread_mutex_init(&p->mu, NULL);
+    pthread_cond_init(&p->cv_work, NULL);
+    pthread_cond_init(&p->cv_done, NULL);
+    for (p->n = 0; p->n < threads && p->n < 16; p->n++)
+        if (pthread_create(&p->th[p->n], NULL, io_worker, p))
+            break;
+    if (p->n == 0) {
+        free(p);
+        return NULL;
+    }
+    return p;
+}
+
+static void io_pool_destroy(io_pool *p)
+{
+    if (!p)
+        return;
+    pthread_mutex_lock(&p->mu);
+    p->stop = true;
+    pthread_cond_broadcast(&p->cv_work);
+    pthread_mutex_unlock(&p->mu);
+    for (int i = 0; i < p->n; i++)
+        pthread_join(p->th[i], NULL);
+    pthread_mutex_destroy(&p->mu);
+    pthread_cond_destroy(&p->cv_work);
+    pthread_cond_destroy(&p->cv_done);
+    free(p);
+}
+
+/* file bytes [off, off + len) -> dst, all workers; 0 ok, 1 read error, 2 unexpected EOF */
+static int io_pool_read(io_pool *p, int fd, uint8_t *dst, size_t off, size_t len)
+{
+    pthread_mutex_lock(&p->mu);
+    p->fd = fd;
+    p->dst = dst;
+    p->off = off;
+    p->len = len;
+    p->next = 0;
+    p->piece = MAX((size_t)1 << 20, (len / (size_t)p->n + 4095) & ~(size_t)4095);
+    p->pending = (int)((len + p->piece - 1) / p->piece);
+    p->err = 0;
+    pthread_cond_broadcast(&p->cv_work);
+    while (p->pending)
+        pthread_cond_wait(&p->cv_done, &p->mu);
+    const int err = p->err;
+    p->len = p->next = 0;
+    pthread_mutex_unlock(&p->mu);
+    return err;
+}
+
 /* ------------------------------------------------------------------ pinned host buffers, allocated on first use */
 static bool ensure_stage(zseek_reader_t *r, char *errbuf)
 {
@@ -412,7 +529,12 @@ static bool h2d_range(zseek_reader_t *r, size_t file_off, size_t bytes, uint8_t 
             r->stage_inflight = 0;
         }
         uint8_t *st = r->h_stage + (size_t)r->stage_next * r->stage_half;
-        ssize_t got = r->user_file.pread(st, n, file_off + done, r->user_file.user_data, call_data);
+        ssize_t got;
+        if (r->file_fd >= 0 && n >= ((size_t)4 << 20) && (r->io || (r->io = io_pool_create((int)env_size("ZSEEK_B200_IO_THREADS", 8))))) {
+            const int e = io_pool_read(r->io, r->file_fd, st, file_off + done, n);
+            got = e == 0 ? (ssize_t)n : e == 2 ? 0 : -1;
+        } else
+            got = r->user_file.pread(st, n, file_off + done, r->user_file.user_data, call_data);
         if (got != (ssize_t)n) {
             zsk_cuda_stream_sync(r->cx, ZSK_STREAM_H2D);
             r->stage_inflight = 0;
@@ -619,6 +741,7 @@ static void reader_free(zseek_reader_t *r)
         return;
     if (r->cx)
         prefetch_drop(r);
+    io_pool_destroy(r->io);
     if (r->cx) {
         zsk_cuda_stream_sync(r->cx, ZSK_STREAM_COMPUTE);
         zsk_cuda_stream_sync(r->cx, ZSK_STREAM_H2D);
@@ -762,13 +885,21 @@ zseek_reader_t *zseek_reader_open_full(zseek_read_file_t user_file, size_t cache
     }
     pthread_mutex_init(&r->lock, NULL);
     r->user_file = user_file;
+    r->file_fd = -1;
     return reader_open_common(r, cache_size, call_data, errbuf);
 }
 
 zseek_reader_t *zseek_reader_open(FILE *cfile, size_t cache_size, void *call_data, char errbuf[ZSEEK_ERRBUF_SIZE])
 {
-    zseek_read_file_t uf = { cfile, file_pread, file_fsize };
-    return zseek_reader_open_full(uf, cache_size, call_data, errbuf);
+    zseek_reader_t *r = calloc(1, sizeof(*r));
+    if (!r) {
+        set_error(errbuf, "allocate reader: %s", strerror(errno));
+        return NULL;
+    }
+    pthread_mutex_init(&r->lock, NULL);
+    r->user_file = (zseek_read_file_t){ cfile, file_pread, file_fsize };
+    r->file_fd = cfile ? fileno(cfile) : -1; /* large ingests read the descriptor with pread(2) from worker threads */
+    return reader_open_common(r, cache_size, call_data, errbuf);
 }
 
 zseek_reader_t *zseek_b200_reader_open_mem(const void *image, size_t size, size_t cache_size, char errbuf[ZSEEK_ERRBUF_SIZE])
@@ -781,6 +912,7 @@ zseek_reader_t *zseek_b200_reader_open_mem(const void *image, size_t size, size_
     pthread_mutex_init(&r->lock, NULL);
     r->mem_image = image;
     r->mem_size = size;
+    r->file_fd = -1;
     r->user_file = (zseek_read_file_t){ r, mem_pread, mem_fsize };
     return reader_open_common(r, cache_size, NULL, errbuf);
 }

@@ -28,6 +28,55 @@
 
 #define ZSK_FULL 0xffffffffu
 
+/* ---- cp.async (LDGSTS): 16-byte global -> shared copies that occupy no registers and stall nobody */
+#ifdef ZSK_EMU
+#include <vector>
+/* The emulator models the WORST legal timing: the source is read when the copy is issued, the destination is
+ * written only when a wait proves the group complete. */
+struct zsk_emu_cp { void *dst; uint8_t data[16]; unsigned group; };
+struct zsk_emu_cpq { std::vector<zsk_emu_cp> pend; unsigned committed = 0; };
+static zsk_emu_cpq zsk_emu_cpqs[1024];
+static inline void zsk_cp16(void *sdst, const void *gsrc)
+{
+    zsk_emu_cpq &q = zsk_emu_cpqs[(unsigned)threadIdx.x];
+    zsk_emu_cp c;
+    c.dst = sdst;
+    memcpy(c.data, gsrc, 16);
+    c.group = q.committed;
+    q.pend.push_back(c);
+}
+static inline void zsk_cp16_cg(void *sdst, const void *gsrc) { zsk_cp16(sdst, gsrc); }
+static inline void zsk_cp_commit() { zsk_emu_cpqs[(unsigned)threadIdx.x].committed++; }
+template <unsigned N> static inline void zsk_cp_wait()
+{
+    zsk_emu_cpq &q = zsk_emu_cpqs[(unsigned)threadIdx.x];
+    size_t k = 0;
+    for (auto &c : q.pend) {
+        if (c.group + N < q.committed) memcpy(c.dst, c.data, 16);
+        else q.pend[k++] = c;
+    }
+    q.pend.resize(k);
+}
+static inline void zsk_cp_reset() { zsk_emu_cpqs[(unsigned)threadIdx.x] = zsk_emu_cpq(); }
+#else
+static __device__ __forceinline__ void zsk_cp16(void *sdst, const void *gsrc)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(sdst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+/* same, cached in L2 only: streams that are read once must not evict what lives in L1 */
+static __device__ __forceinline__ void zsk_cp16_cg(void *sdst, const void *gsrc)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(sdst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+static __device__ __forceinline__ void zsk_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <unsigned N> static __device__ __forceinline__ void zsk_cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+static __device__ __forceinline__ void zsk_cp_reset() {}
+#endif
+
+
+
 static __device__ __forceinline__ uint32_t zsk_rd16(const uint8_t *p) { return (uint32_t)ZSK_LDG(p) | ((uint32_t)ZSK_LDG(p + 1) << 8); }
 static __device__ __forceinline__ uint32_t zsk_rd24(const uint8_t *p) { return zsk_rd16(p) | ((uint32_t)ZSK_LDG(p + 2) << 16); }
 static __device__ __forceinline__ uint32_t zsk_rd32(const uint8_t *p) { return zsk_rd16(p) | (zsk_rd16(p + 2) << 16); }

@@ -352,6 +352,39 @@ def test_reference_example_binary_runs_against_b200_reader(flag, tmp_path, torch
     assert p.returncode == 0 and "SUCCESS" in p.stdout, (p.stdout, p.stderr)
 
 
+@pytest.mark.skipif(not have_reference(), reason="oracle/_ref/libzseek_ref.so missing")
+@pytest.mark.parametrize("codec,level,frame", [(LZ4, 0, 65536), (ZSTD, 3, 262144)])
+def test_file_opened_by_path_uses_parallel_ingest_and_decodes_identically(lib, codec, level, frame, tmp_path, torch_cuda):
+    """n2: zseek_reader_open(FILE*) pulls large ranges of the file with pread(2) from worker threads into the pinned staging
+    halves (the callback path stays as it is).  A 192 MiB file read by path — whole-file decode to device memory, a
+    multi-frame host range, plain zseek_preads — must give the writer's input, with 1 and with 8 I/O threads; the
+    caller's FILE position is left where it was."""
+    torch = torch_cuda
+    import os
+    from datagen import refwriter, zsyn
+    data = zsyn.gen_parallel(192 << 20)
+    image = refwriter.write_parallel(data, codec, level, frame, piece_frames=max(1, (8 << 20) // frame))
+    path = tmp_path / "big.zsk"
+    path.write_bytes(image)
+    want = np.frombuffer(data, dtype=np.uint8)
+    for threads in ("1", "8"):
+        os.environ["ZSEEK_B200_IO_THREADS"] = threads
+        try:
+            with lib.Reader(path=str(path), cache_size=0) as rd:
+                assert rd.size == len(data)
+                dev = torch.zeros(rd.size + 64, dtype=torch.uint8, device="cuda")
+                assert rd.decode_frames(0, rd.frames, dev) == rd.size
+                assert bool((dev[:rd.size] == torch.from_numpy(want.copy()).cuda()).all())
+                host = np.zeros(50 << 20, dtype=np.uint8)
+                assert rd.read_range_into(host, host.size, 7 << 20) == host.size
+                assert (host == want[7 << 20:(7 << 20) + host.size]).all()
+                for off in (0, 123456789, rd.size - 100):
+                    r, b = rd.pread(70000, off)
+                    assert b == data[off:off + r] and r > 0
+        finally:
+            del os.environ["ZSEEK_B200_IO_THREADS"]
+
+
 # --------------------------------------------------------------------------- every LZ4 kernel, whatever the launch size
 LZ4_KERNEL_ENVS = {
     "lane_per_frame": {"ZSEEK_B200_LZ4_LANE_MIN": "0", "ZSEEK_B200_SORT_MIN": "0"},           # the kernel big launches get

@@ -64,6 +64,64 @@ def _gather_worker(rank, world, port, image_path, q):
     dist.destroy_process_group()
 
 
+def _pipeline_worker(rank, world, port, image_path, q):
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    from libzseek_b200.sharding import chunk_plan, decode_and_gather, shard_range
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    image = open(image_path, "rb").read()
+    with OraclePort(image) as op:  # stands in for the per-rank GPU decode of chunk [f0, f1)
+        full = op.decode_all()
+        d_off = op.d_off
+        calls = []
+
+        def decode_chunk(f0, f1, view):
+            calls.append((f0, f1))
+            view.copy_(torch.from_numpy(full[int(d_off[f0]):int(d_off[f1])].copy()))
+
+        lo, hi = shard_range(op.frames, rank, world)
+        out = torch.zeros(op.size, dtype=torch.uint8) if rank == 0 else None
+        local = torch.zeros(int(d_off[hi] - d_off[lo]), dtype=torch.uint8) if rank != 0 else None
+        got = decode_and_gather(decode_chunk, d_off, out=out, local=local, dst_rank=0, chunk_bytes=50000)
+        assert calls == chunk_plan(d_off, lo, hi, 50000) and len(calls) > 1
+        if rank == 0:
+            q.put(bool((got.numpy() == full).all()))
+        else:
+            assert got is None
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_chunk_plan_covers_the_range():
+    from libzseek_b200.sharding import chunk_plan
+    d_off = np.cumsum([0] + [100, 100, 250, 40, 1000, 5, 5, 5]).astype(np.uint64)
+    for lo, hi in ((0, 8), (2, 7), (3, 3)):
+        plan = chunk_plan(d_off, lo, hi, 300)
+        assert [a for a, _ in plan] == [lo] * bool(plan) + [b for _, b in plan][:-1]
+        assert (not plan and lo == hi) or plan[-1][1] == hi
+        for a, b in plan:
+            assert b > a and (b - a == 1 or int(d_off[b] - d_off[a]) <= 300)
+
+
+def test_decode_and_gather_pipeline_over_gloo_world2(tmp_path):
+    """The chunked 'decode chunk j -> send chunk j' pipeline on CPU: rank 0 ends up with the whole file, byte-exact."""
+    import torch.multiprocessing as mp
+    from conftest import GOLDEN
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_pipeline_worker, args=(r, 2, port, os.path.join(GOLDEN, "mix_zstd3.zsk"), q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    ok = q.get(timeout=120)
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    assert ok
+
+
 def test_gather_to_over_gloo_world2(tmp_path):
     """N>1 path on CPU: each rank holds the decoded bytes of its frame shard, rank 0 ends up with the
     whole file, byte-exact."""
