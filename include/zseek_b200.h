@@ -69,6 +69,22 @@ ZSEEK_EXPORT ssize_t zseek_b200_pread_batch(zseek_reader_t *reader, size_t n, co
                                             const uint64_t *dst_offs, uint64_t dst_stride, int64_t *results,
                                             void *call_data, char errbuf[ZSEEK_ERRBUF_SIZE]);
 
+/* Stream-ordered batch: the same n reads, but every array lives in DEVICE memory (dev_offsets,
+ * dev_counts or NULL + fixed_count, dev_dst with dev_dst_offs or dst_stride, optional dev_results) and nothing is
+ * copied to or from the host: lookup, the list of touched frames, their decode (each only up to the last byte the
+ * batch needs of it) and the gather are queued on `stream` — a cudaStream_t passed as void*, NULL = the reader's own
+ * stream — and the call returns without waiting.  Work queued on `stream` afterwards sees dev_dst / dev_results
+ * complete.  The compressed bytes of the reader's shard must be resident (zseek_b200_load); frames are decoded into a
+ * batch slab of the reader, not into the LRU cache.  Results are defined exactly like zseek_b200_pread_batch.
+ * zseek_b200_batch_wait waits for the most recent async batch and returns 0, or -1 with the first frame error
+ * ("decompress frame: ...", "frame outside this reader's shard"); dev_dst of requests in failed frames is undefined.
+ * One async batch per reader may be in flight (the next call waits for the previous one). */
+ZSEEK_EXPORT ssize_t zseek_b200_pread_batch_async(zseek_reader_t *reader, size_t n, const uint64_t *dev_offsets,
+                                                  const uint64_t *dev_counts, uint64_t fixed_count, void *dev_dst,
+                                                  const uint64_t *dev_dst_offs, uint64_t dst_stride, int64_t *dev_results,
+                                                  void *stream, char errbuf[ZSEEK_ERRBUF_SIZE]);
+ZSEEK_EXPORT int zseek_b200_batch_wait(zseek_reader_t *reader, char errbuf[ZSEEK_ERRBUF_SIZE]);
+
 /* Forgets the HBM-resident compressed image (the next read pulls its frames again). */
 ZSEEK_EXPORT void zseek_b200_unload(zseek_reader_t *reader);
 

@@ -114,6 +114,17 @@ struct zseek_reader {
     uint8_t *g_out; /* device staging for host destinations */
     size_t g_out_cap;
 
+    /* stream-ordered batches (zseek_b200_pread_batch_async): slab of bs_cap decoded-frame slots, job arrays filled on the
+     * device by zsk_compact_kernel, per-frame slot map, {job count, error flag} */
+    uint8_t *g_bslab;
+    uint32_t bs_cap;
+    uint32_t *g_bjob_ids, *g_bjob_limits, *g_bctl;
+    uint64_t *g_bjob_offs;
+    int32_t *g_bjob_status;
+    int64_t *g_bsrc;
+    int async_stream;        /* ZSK_STREAM_COMPUTE or ZSK_STREAM_USER of the batch in flight; -1 = none */
+    uint32_t async_jobs_max;
+
     /* read-ahead */
     uint64_t ra_next;
     uint32_t ra_window, ra_max;
@@ -742,13 +753,15 @@ static void reader_free(zseek_reader_t *r)
     if (r->cx)
         prefetch_drop(r);
     io_pool_destroy(r->io);
+    if (r->cx && r->async_stream >= 0)
+        zsk_cuda_stream_sync(r->cx, r->async_stream);
     if (r->cx) {
         zsk_cuda_stream_sync(r->cx, ZSK_STREAM_COMPUTE);
         zsk_cuda_stream_sync(r->cx, ZSK_STREAM_H2D);
         zsk_cuda_stream_sync(r->cx, ZSK_STREAM_D2H);
         void *dev[] = { r->g_coff, r->g_doff, r->g_comp, r->g_slab, r->g_frame_src, r->g_job_ids, r->g_job_offs, r->g_job_status, r->g_job_limits,
                         r->g_b_offsets, r->g_b_counts, r->g_b_dstoffs, r->g_b_frame, r->g_b_inframe, r->g_b_nbytes, r->g_touched,
-                        r->g_out };
+                        r->g_out, r->g_bslab, r->g_bjob_ids, r->g_bjob_limits, r->g_bctl, r->g_bjob_offs, r->g_bjob_status, r->g_bsrc };
         for (size_t i = 0; i < sizeof(dev) / sizeof(dev[0]); i++)
             zsk_cuda_free(r->cx, dev[i]);
         void *pin[] = { r->h_stage, r->h_mirror, r->h_job_ids, r->h_job_offs, r->h_job_status, r->h_job_limits };
@@ -803,6 +816,7 @@ static zseek_reader_t *reader_open_common(zseek_reader_t *r, size_t cache_size, 
         goto fail;
     }
     uint64_t N = r->nframes;
+    r->async_stream = -1;
     r->shard_lo = 0;
     r->shard_hi = N;
     r->user_cache_size = cache_size;
@@ -1587,7 +1601,7 @@ ssize_t zseek_b200_pread_batch(zseek_reader_t *r, size_t n, const uint64_t *offs
     }
     /* touched frames, ascending; processed in groups that fit the decoded-frame cache */
     zsk_gather_args ga = { r->g_b_frame, r->g_b_inframe, r->g_b_nbytes, r->g_frame_src, r->g_slab + ZSK_PAD_FRONT, gdst,
-                           dst_offs ? r->g_b_dstoffs : NULL, dst_stride, (uint32_t)n };
+                           dst_offs ? r->g_b_dstoffs : NULL, dst_stride, (uint32_t)n, NULL };
     uint64_t f = 0;
     while (f < N) {
         uint32_t in_group = 0, nmiss = 0;
@@ -1653,6 +1667,142 @@ ssize_t zseek_b200_pread_batch(zseek_reader_t *r, size_t n, const uint64_t *offs
     ret = (ssize_t)n;
 out:
     free(nb);
+    pthread_mutex_unlock(&r->lock);
+    return ret;
+}
+
+/* ------------------------------------------------------------------ stream-ordered batch */
+static int batch_wait_locked(zseek_reader_t *r, char *errbuf)
+{
+    if (r->async_stream < 0)
+        return 0;
+    const int sidx = r->async_stream;
+    r->async_stream = -1;
+    uint32_t ctl[2] = { 0, 0 };
+    if (zsk_cuda_memcpy_async(r->cx, ctl, r->g_bctl, sizeof(ctl), ZSK_D2H, sidx) || zsk_cuda_stream_sync(r->cx, sidx)) {
+        cuda_fail(r, errbuf, "batch");
+        return -1;
+    }
+    if (ctl[1]) {
+        set_error(errbuf, ctl[1] == 1 ? "frame outside this reader's shard" : "batch touches more frames than the slab holds");
+        return -1;
+    }
+    const uint32_t njobs = MIN(ctl[0], r->async_jobs_max);
+    if (njobs == 0)
+        return 0;
+    int32_t *st = malloc(njobs * sizeof(int32_t));
+    if (!st) {
+        set_error(errbuf, "allocate statuses");
+        return -1;
+    }
+    int rc = 0;
+    if (zsk_cuda_memcpy_async(r->cx, st, r->g_bjob_status, njobs * sizeof(int32_t), ZSK_D2H, sidx) || zsk_cuda_stream_sync(r->cx, sidx)) {
+        cuda_fail(r, errbuf, "batch");
+        rc = -1;
+    } else
+        for (uint32_t i = 0; i < njobs; i++)
+            if (st[i] != ZSK_ST_OK) {
+                set_error(errbuf, "decompress frame: %s", status_name(st[i]));
+                rc = -1;
+                break;
+            }
+    free(st);
+    return rc;
+}
+
+int zseek_b200_batch_wait(zseek_reader_t *r, char errbuf[ZSEEK_ERRBUF_SIZE])
+{
+    if (!r) {
+        set_error(errbuf, "invalid reader");
+        return -1;
+    }
+    pthread_mutex_lock(&r->lock);
+    int rc = batch_wait_locked(r, errbuf);
+    pthread_mutex_unlock(&r->lock);
+    return rc;
+}
+
+ssize_t zseek_b200_pread_batch_async(zseek_reader_t *r, size_t n, const uint64_t *dev_offsets, const uint64_t *dev_counts,
+                                     uint64_t fixed_count, void *dev_dst, const uint64_t *dev_dst_offs, uint64_t dst_stride,
+                                     int64_t *dev_results, void *stream, char errbuf[ZSEEK_ERRBUF_SIZE])
+{
+    if (!r) {
+        set_error(errbuf, "invalid reader");
+        return -1;
+    }
+    if (n == 0)
+        return 0;
+    if (n > 0x7fffffffu) {
+        set_error(errbuf, "batch too large");
+        return -1;
+    }
+    pthread_mutex_lock(&r->lock);
+    ssize_t ret = -1;
+    char scratch[ZSEEK_ERRBUF_SIZE];
+    prefetch_drop(r);
+    batch_wait_locked(r, scratch); /* one async batch in flight: its buffers are about to be reused */
+    const uint64_t N = r->nframes, nshard = r->shard_hi - r->shard_lo;
+    if (!(r->shard_lo >= r->res_lo && r->shard_hi <= r->res_hi) && nshard) {
+        set_error(errbuf, "compressed image not resident: call zseek_b200_load first");
+        goto out;
+    }
+    if (!ensure_batch(r, n, errbuf))
+        goto out;
+    const uint32_t need = (uint32_t)MIN((uint64_t)n, nshard);
+    if (!r->g_bsrc &&
+        (zsk_cuda_malloc(r->cx, (void **)&r->g_bsrc, (N + 1) * sizeof(int64_t)) || zsk_cuda_malloc(r->cx, (void **)&r->g_bctl, 2 * sizeof(uint32_t)))) {
+        cuda_fail(r, errbuf, "allocate batch buffers");
+        goto out;
+    }
+    if (need > r->bs_cap) {
+        zsk_cuda_stream_sync(r->cx, ZSK_STREAM_COMPUTE);
+        void *old[] = { r->g_bslab, r->g_bjob_ids, r->g_bjob_limits, r->g_bjob_offs, r->g_bjob_status };
+        for (size_t i = 0; i < 5; i++)
+            zsk_cuda_free(r->cx, old[i]);
+        r->g_bslab = NULL; r->g_bjob_ids = r->g_bjob_limits = NULL; r->g_bjob_offs = NULL; r->g_bjob_status = NULL;
+        r->bs_cap = 0;
+        const uint32_t cap = (uint32_t)MIN(nshard, MAX((uint64_t)need, (uint64_t)1024));
+        if (zsk_cuda_malloc(r->cx, (void **)&r->g_bslab, (size_t)cap * r->slot_size + ZSK_PAD_FRONT + ZSK_PAD_BACK) ||
+            zsk_cuda_malloc(r->cx, (void **)&r->g_bjob_ids, cap * sizeof(uint32_t)) ||
+            zsk_cuda_malloc(r->cx, (void **)&r->g_bjob_limits, cap * sizeof(uint32_t)) ||
+            zsk_cuda_malloc(r->cx, (void **)&r->g_bjob_offs, cap * sizeof(uint64_t)) ||
+            zsk_cuda_malloc(r->cx, (void **)&r->g_bjob_status, cap * sizeof(int32_t))) {
+            cuda_fail(r, errbuf, "allocate batch slab");
+            goto out;
+        }
+        r->bs_cap = cap;
+    }
+    const int sidx = stream ? ZSK_STREAM_USER : ZSK_STREAM_COMPUTE;
+    if (stream)
+        zsk_cuda_set_user_stream(r->cx, stream);
+    zsk_lookup_args la = { r->g_doff, (uint32_t)N, dev_offsets, dev_counts, fixed_count, (uint32_t)n,
+                           r->g_b_frame, r->g_b_inframe, r->g_b_nbytes, r->g_touched };
+    zsk_compact_args ca = { r->g_touched, (uint32_t)N, (uint32_t)r->shard_lo, (uint32_t)r->shard_hi, r->slot_size, r->bs_cap,
+                            r->g_bjob_ids, r->g_bjob_offs, r->g_bjob_limits, r->g_bsrc, r->g_bctl, r->g_bctl + 1 };
+    zsk_decode_args da;
+    fill_decode_args(r, &da);
+    da.frame_ids = r->g_bjob_ids;
+    da.dst_offs = r->g_bjob_offs;
+    da.dst = r->g_bslab + ZSK_PAD_FRONT;
+    da.njobs = need;
+    da.njobs_dev = r->g_bctl;
+    da.status = r->g_bjob_status;
+    da.limits = r->partial_decode ? r->g_bjob_limits : NULL;
+    da.dsize_sum = (uint64_t)need * r->max_dsize;
+    zsk_gather_args ga = { r->g_b_frame, r->g_b_inframe, r->g_b_nbytes, r->g_bsrc, r->g_bslab + ZSK_PAD_FRONT, dev_dst,
+                           dev_dst_offs, dst_stride, (uint32_t)n, dev_results };
+    if (zsk_cuda_memset_async(r->cx, r->g_touched, 0, (N + 1) * sizeof(uint32_t), sidx) ||
+        zsk_cuda_memset_async(r->cx, r->g_bctl, 0, 2 * sizeof(uint32_t), sidx) ||
+        zsk_cuda_launch_lookup(r->cx, &la, sidx) || zsk_cuda_launch_compact(r->cx, &ca, sidx) ||
+        (need && zsk_cuda_launch_decode(r->cx, r->codec, &da, sidx)) || zsk_cuda_launch_gather(r->cx, &ga, sidx)) {
+        cuda_fail(r, errbuf, "queue batch");
+        zsk_cuda_stream_sync(r->cx, sidx);
+        goto out;
+    }
+    r->async_stream = sidx;
+    r->async_jobs_max = need;
+    ret = (ssize_t)n;
+out:
     pthread_mutex_unlock(&r->lock);
     return ret;
 }

@@ -64,6 +64,10 @@ typedef struct zsk_decode_args {
     uint64_t dsize_sum;         /* sum of the jobs' decompressed sizes (sizes the zstd pipeline's scratch pools); 0 = unknown */
     const uint32_t *job_list;   /* launch-layer internal: when set, only jobs job_list[0 .. *job_list_count) are run */
     const unsigned long long *job_list_count;
+    const uint32_t *njobs_dev;  /* optional: the job count lives in device memory (written by an earlier kernel of the same
+                                 * stream); njobs is then an upper bound that sizes grids and scratch, and the launch runs
+                                 * jobs [0, min(njobs, *njobs_dev - job_base)) */
+    uint32_t job_base;
 } zsk_decode_args;
 
 /* K1: batched offset -> frame lookup (semantics of reference src/seek_table.c:187-202 + decompress.c:445) */
@@ -92,15 +96,24 @@ typedef struct zsk_gather_args {
     const uint64_t *dst_offs;
     uint64_t dst_stride;
     uint32_t n;
+    int64_t *results;            /* optional [n]: nbytes of every request, as zseek_pread would return it */
 } zsk_gather_args;
 
-/* frames that are touched by a batch but not resident in the decoded-frame cache */
+/* Turns the per-frame marks of K1 into the job list of a stream-ordered batch: every touched frame gets a job (frame id,
+ * limit = how much of it the batch needs, a slot of the batch slab) and its slot offset in frame_src; untouched frames
+ * get frame_src = -1. */
 typedef struct zsk_compact_args {
-    const uint32_t *touched;   /* [N] */
-    const int64_t *frame_src;  /* [N] */
+    const uint32_t *touched;   /* [N] from K1 */
     uint32_t nframes;
-    uint32_t *out_ids;         /* [N] */
-    uint32_t *out_count;       /* zero-initialised */
+    uint32_t shard_lo, shard_hi; /* frames outside [shard_lo, shard_hi) set *error */
+    uint64_t slot_size;
+    uint32_t max_jobs;         /* capacity of the job arrays / slab slots */
+    uint32_t *job_ids;         /* [max_jobs] out */
+    uint64_t *job_offs;        /* [max_jobs] out: slot offset inside the slab */
+    uint32_t *job_limits;      /* [max_jobs] out */
+    int64_t *frame_src;        /* [N] out */
+    uint32_t *count;           /* zero-initialised; out: number of jobs */
+    uint32_t *error;           /* zero-initialised; out: 1 = frame outside the shard, 2 = more touched frames than max_jobs */
 } zsk_compact_args;
 
 #ifdef __cplusplus

@@ -28,6 +28,14 @@
 
 #define ZSK_FULL 0xffffffffu
 
+/* jobs of this launch: the host's count, or what an earlier kernel of the stream left in device memory */
+static __device__ __forceinline__ uint32_t zsk_njobs(const zsk_decode_args &a)
+{
+    if (!a.njobs_dev) return a.njobs;
+    const uint32_t n = *a.njobs_dev;
+    return n > a.job_base ? min(a.njobs, n - a.job_base) : 0u;
+}
+
 /* ---- cp.async (LDGSTS): 16-byte global -> shared copies that occupy no registers and stall nobody */
 #ifdef ZSK_EMU
 #include <vector>

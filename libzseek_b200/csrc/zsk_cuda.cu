@@ -20,7 +20,7 @@
 struct zsk_cuda_ctx {
     int device;
     int sm_count;
-    cudaStream_t streams[ZSK_NSTREAMS];
+    cudaStream_t streams[ZSK_NSTREAMS + 1];   /* + ZSK_STREAM_USER: caller-owned, never created or destroyed here */
     cudaEvent_t sync_ev;                 /* cross-stream dependencies */
     cudaEvent_t user_ev[ZSK_NEVENTS];
     cudaEvent_t t0, t1;                  /* zsk_cuda_timer_* */
@@ -36,6 +36,8 @@ struct zsk_cuda_ctx {
     uint32_t *zdeferred;
     size_t zjobs_cap;
     zsk_zblock *zblocks;
+    uint32_t *zbprog;                    /* 2 words per block descriptor (launches with limits) */
+    size_t zbprog_cap;
     uint32_t *zseqs;
     uint8_t *zlits;
     size_t zblocks_cap, zseqs_cap, zlits_cap;
@@ -189,7 +191,7 @@ void zsk_cuda_ctx_destroy(zsk_cuda_ctx *cx)
     cudaEventDestroy(cx->k1);
     cudaFree(cx->counters);
     cudaFree(cx->scratch);
-    cudaFree(cx->zframes); cudaFree(cx->zdeferred); cudaFree(cx->zblocks); cudaFree(cx->zseqs); cudaFree(cx->zlits); cudaFree(cx->zctr);
+    cudaFree(cx->zbprog); cudaFree(cx->zframes); cudaFree(cx->zdeferred); cudaFree(cx->zblocks); cudaFree(cx->zseqs); cudaFree(cx->zlits); cudaFree(cx->zctr);
     free(cx);
 }
 
@@ -214,6 +216,7 @@ void zsk_cuda_trace_dump(zsk_cuda_ctx *cx)
 }
 
 const char *zsk_cuda_error(zsk_cuda_ctx *cx) { return cx ? cx->err : "no device context"; }
+void zsk_cuda_set_user_stream(zsk_cuda_ctx *cx, void *stream) { cx->streams[ZSK_STREAM_USER] = (cudaStream_t)stream; }
 int zsk_cuda_device(const zsk_cuda_ctx *cx) { return cx->device; }
 int zsk_cuda_sm_count(const zsk_cuda_ctx *cx) { return cx->sm_count; }
 unsigned long long zsk_cuda_launch_count(const zsk_cuda_ctx *cx) { return cx->launches; }
@@ -366,6 +369,11 @@ static int launch_zstd_pipeline(zsk_cuda_ctx *cx, zsk_decode_args a, cudaStream_
     if ((rc = grow_pool(cx, (void **)&cx->zseqs, &cap_s, want_seqs * 3 * sizeof(uint32_t)))) return rc;
     if ((rc = grow_pool(cx, (void **)&cx->zlits, &cap_l, want_lits + ZSK_PAD_BACK))) return rc;
     cx->zblocks_cap = cap_b / sizeof(zsk_zblock);
+    if (a.limits) {
+        size_t cap_p = cx->zbprog_cap * 2 * sizeof(uint32_t);
+        if ((rc = grow_pool(cx, (void **)&cx->zbprog, &cap_p, cx->zblocks_cap * 2 * sizeof(uint32_t)))) return rc;
+        cx->zbprog_cap = cap_p / (2 * sizeof(uint32_t));
+    }
     cx->zseqs_cap = cap_s / (3 * sizeof(uint32_t));
     cx->zlits_cap = cap_l - ZSK_PAD_BACK;
 
@@ -375,6 +383,7 @@ static int launch_zstd_pipeline(zsk_cuda_ctx *cx, zsk_decode_args a, cudaStream_
     z.blocks_cap = cx->zblocks_cap; z.seqs_cap = cx->zseqs_cap; z.lits_cap = cx->zlits_cap;
     z.ctr = cx->zctr + (size_t)(cx->zctr_next++ % ZSK_NCOUNTERS) * ZSK_ZC_N;
     z.deferred = cx->zdeferred;
+    z.bprog = cx->zbprog;
     CK(cx, cudaMemsetAsync(z.ctr, 0, ZSK_ZC_N * sizeof(unsigned long long), s));
     zsk_zstd_index_kernel<<<(unsigned)((njobs + 127) / 128), 128, 0, s>>>(z);
     zsk_zstd_fse_kernel<<<cx->zfse_ctas, ZSK_ZFSE_THREADS, ZSK_ZFSE_SMEM, s>>>(z);
@@ -402,6 +411,7 @@ int zsk_cuda_launch_decode(zsk_cuda_ctx *cx, int codec, const zsk_decode_args *a
     if (rc) return rc;
     a.job_list = NULL;
     a.job_list_count = NULL;
+    if (!a.njobs_dev) a.job_base = 0;
     cudaStream_t s = cx->streams[stream];
     CK(cx, cudaEventRecord(cx->k0, s));
     if (codec == ZSK_CODEC_LZ4 && a.njobs >= cx->lz4_lane_min) {
@@ -435,6 +445,7 @@ int zsk_cuda_launch_decode(zsk_cuda_ctx *cx, int codec, const zsk_decode_args *a
             if (a.dst_offs) w.dst_offs = a.dst_offs + j0;
             if (a.limits) w.limits = a.limits + j0;
             w.status = a.status + j0;
+            w.job_base = a.job_base + j0;
             w.dsize_sum = (uint64_t)((double)dsum * (double)w.njobs / (double)total) + 1u;
             rc = launch_zstd_pipeline(cx, w, s, stream);
             if (rc) return rc;

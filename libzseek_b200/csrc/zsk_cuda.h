@@ -15,7 +15,7 @@ extern "C" {
 typedef struct zsk_cuda_ctx zsk_cuda_ctx;
 
 /* streams of a context */
-enum { ZSK_STREAM_COMPUTE = 0, ZSK_STREAM_H2D = 1, ZSK_STREAM_D2H = 2, ZSK_NSTREAMS = 3 };
+enum { ZSK_STREAM_COMPUTE = 0, ZSK_STREAM_H2D = 1, ZSK_STREAM_D2H = 2, ZSK_NSTREAMS = 3, ZSK_STREAM_USER = 3 };
 /* copy kinds */
 enum { ZSK_H2D = 1, ZSK_D2H = 2, ZSK_D2D = 3 };
 
@@ -35,6 +35,8 @@ int zsk_cuda_free_host(zsk_cuda_ctx *cx, void *p);
 int zsk_cuda_memset_async(zsk_cuda_ctx *cx, void *p, int v, size_t n, int stream);
 int zsk_cuda_memcpy_async(zsk_cuda_ctx *cx, void *dst, const void *src, size_t n, int kind, int stream);
 int zsk_cuda_stream_sync(zsk_cuda_ctx *cx, int stream);
+/* ZSK_STREAM_USER: a caller-owned cudaStream_t (NULL = the legacy default stream) that stream-ordered calls enqueue on */
+void zsk_cuda_set_user_stream(zsk_cuda_ctx *cx, void *stream);
 int zsk_cuda_stream_wait(zsk_cuda_ctx *cx, int waiter, int signaler); /* waiter waits for work queued on signaler so far */
 /* a small pool of user events: record on a stream, block the host until it has completed */
 #define ZSK_NEVENTS 8

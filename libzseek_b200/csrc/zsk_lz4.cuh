@@ -263,7 +263,7 @@ __global__ void __launch_bounds__(ZSK_LZ4_CTA_THREADS) zsk_lz4_decode_batch_kern
         } else { /* ZSK_LZ4_W_FETCH */
             if (lane == 0) job = atomicAdd(a.work_counter, 1u);
             job = __shfl_sync(ZSK_FULL, job, 0);
-            if (job >= a.njobs) break;
+            if (job >= zsk_njobs(a)) break;
             const uint32_t f = a.frame_ids ? a.frame_ids[job] : a.first_frame + job;
             const uint64_t c0 = a.c_off[f], c1 = a.c_off[f + 1], d0 = a.d_off[f], d1 = a.d_off[f + 1];
             src = a.comp + (c0 - a.comp_base);

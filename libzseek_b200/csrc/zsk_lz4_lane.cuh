@@ -404,7 +404,7 @@ __global__ void __launch_bounds__(ZSK_LZ4L_THREADS) zsk_lz4_decode_lane_kernel(z
         }
         if (phase == ZSK_L_FETCH) {
             job = atomicAdd(a.work_counter, 1u);
-            if (job >= a.njobs) phase = ZSK_L_DONE;
+            if (job >= zsk_njobs(a)) phase = ZSK_L_DONE;
             else {
                 const uint32_t f = a.frame_ids ? a.frame_ids[job] : a.first_frame + job;
                 const uint64_t c0 = a.c_off[f], c1 = a.c_off[f + 1], d0 = a.d_off[f], d1 = a.d_off[f + 1];

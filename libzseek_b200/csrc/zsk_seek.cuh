@@ -55,6 +55,7 @@ __global__ void __launch_bounds__(256) zsk_gather_kernel(zsk_gather_args a)
     for (uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < a.n; i += warps) {
         const int32_t f = a.frame[i];
         const uint32_t nb = a.nbytes[i];
+        if (a.results && lane == 0) a.results[i] = (int64_t)nb;
         if (f < 0 || nb == 0) continue;
         const int64_t so = a.frame_src[f];
         if (so < 0) continue;
@@ -64,9 +65,25 @@ __global__ void __launch_bounds__(256) zsk_gather_kernel(zsk_gather_args a)
     }
 }
 
-/* Compacts the frames a batch needs but the decoded-frame cache does not hold. */
+/* Job list of a stream-ordered batch (zseek_b200_pread_batch_async): see zsk_compact_args. */
 __global__ void __launch_bounds__(256) zsk_compact_kernel(zsk_compact_args a)
 {
-    for (uint32_t f = blockIdx.x * blockDim.x + threadIdx.x; f < a.nframes; f += gridDim.x * blockDim.x)
-        if (a.touched[f] && a.frame_src[f] < 0) a.out_ids[atomicAdd(a.out_count, 1u)] = f;
+    for (uint32_t f = blockIdx.x * blockDim.x + threadIdx.x; f < a.nframes; f += gridDim.x * blockDim.x) {
+        const uint32_t need = a.touched[f];
+        int64_t src = -1;
+        if (need) {
+            if (f < a.shard_lo || f >= a.shard_hi) *a.error = 1u;
+            else {
+                const uint32_t j = atomicAdd(a.count, 1u);
+                if (j >= a.max_jobs) *a.error = 2u;
+                else {
+                    a.job_ids[j] = f;
+                    a.job_offs[j] = (uint64_t)j * a.slot_size;
+                    a.job_limits[j] = need;
+                    src = (int64_t)((uint64_t)j * a.slot_size);
+                }
+            }
+        }
+        a.frame_src[f] = src;
+    }
 }

@@ -747,7 +747,7 @@ __global__ void __launch_bounds__(ZSK_ZSTD_CTA_THREADS, ZSK_ZSTD_MIN_CTAS) zsk_z
         if (a.job_list) { /* the pipeline's deferred frames only */
             if (job >= (uint32_t)*a.job_list_count) break;
             job = a.job_list[job];
-        } else if (job >= a.njobs) break;
+        } else if (job >= zsk_njobs(a)) break;
         const uint32_t f = a.frame_ids ? a.frame_ids[job] : a.first_frame + job;
         const uint64_t c0 = a.c_off[f], c1 = a.c_off[f + 1], d0 = a.d_off[f], d1 = a.d_off[f + 1];
         const uint8_t *src = a.comp + (c0 - a.comp_base);

@@ -77,6 +77,10 @@ def load_library():
     L.zseek_b200_read_range.argtypes = [vp, vp, sz, sz, vp, cp]
     L.zseek_b200_pread_batch.restype = C.c_ssize_t
     L.zseek_b200_pread_batch.argtypes = [vp, sz, vp, vp, C.c_uint64, vp, vp, C.c_uint64, vp, vp, cp]
+    L.zseek_b200_pread_batch_async.restype = C.c_ssize_t
+    L.zseek_b200_pread_batch_async.argtypes = [vp, sz, vp, vp, C.c_uint64, vp, vp, C.c_uint64, vp, vp, cp]
+    L.zseek_b200_batch_wait.restype = C.c_int
+    L.zseek_b200_batch_wait.argtypes = [vp, cp]
     L.zseek_b200_cache_clear.restype = None
     L.zseek_b200_cache_clear.argtypes = [vp]
     L.zseek_b200_unload.restype = None
@@ -264,6 +268,24 @@ class Reader:
         if r < 0:
             raise ZseekError(self.err.value.decode())
         return results
+
+    def pread_batch_async(self, dev_offsets, dev_dst, fixed_count: int = 0, dev_counts=None, dev_dst_offs=None, dst_stride: int = 0,
+                          dev_results=None, stream=None):
+        """zseek_b200_pread_batch_async: every array is a device tensor (uint64 offsets/counts/dst_offs viewed as int64 is
+        fine, int64 results); queued on `stream` (a torch.cuda.Stream, an int cudaStream_t, or None = the reader's own
+        stream); returns at once.  batch_wait() reports frame errors."""
+        n = dev_offsets.numel()
+        sp = stream.cuda_stream if hasattr(stream, "cuda_stream") else (stream or 0)
+        r = self.L.zseek_b200_pread_batch_async(self.h, n, _addr(dev_offsets), _addr(dev_counts) if dev_counts is not None else None,
+                                                fixed_count, _addr(dev_dst), _addr(dev_dst_offs) if dev_dst_offs is not None else None,
+                                                dst_stride, _addr(dev_results) if dev_results is not None else None, sp or None, self.err)
+        if r < 0:
+            raise ZseekError(self.err.value.decode())
+        return r
+
+    def batch_wait(self):
+        if self.L.zseek_b200_batch_wait(self.h, self.err) != 0:
+            raise ZseekError(self.err.value.decode())
 
     def cache_clear(self):
         self.L.zseek_b200_cache_clear(self.h)

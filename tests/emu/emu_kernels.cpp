@@ -30,6 +30,8 @@ static void emu_zstd_pipeline(zsk_decode_args a, uint32_t njobs, uint32_t ctas, 
     std::vector<uint32_t> seqs(3 * z.seqs_cap + 3, 0xEEEEEEEEu);
     std::vector<uint8_t> lits(z.lits_cap + ZSK_PAD_BACK, 0xEE);
     std::vector<uint32_t> deferred(njobs + 1);
+    std::vector<uint32_t> bprog(2 * z.blocks_cap + 2, 0xEEEEEEEEu);
+    z.bprog = bprog.data();
     unsigned long long ctr[ZSK_ZC_N] = { 0 };
     z.frames = frames.data(); z.blocks = blocks.data(); z.seqs = seqs.data(); z.lits = lits.data();
     z.ctr = ctr; z.deferred = deferred.data();

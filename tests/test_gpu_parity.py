@@ -504,6 +504,65 @@ def test_batches_over_partially_decoded_frames(lib, codec, level, frame, torch_c
                 assert rd.pread(100000, off) == rr.pread(100000, off)
 
 
+@pytest.mark.skipif(not have_reference(), reason="oracle/_ref/libzseek_ref.so missing")
+@pytest.mark.parametrize("codec,level,frame", [(LZ4, 0, 65536), (ZSTD, 3, 262144), (ZSTD, 19, 1 << 20)])
+def test_async_batch_on_a_caller_stream_matches_a_loop_of_reference_preads(lib, codec, level, frame, torch_cuda):
+    """n1: zseek_b200_pread_batch_async — request arrays, destination and results in device memory, everything queued on
+    a caller stream, no host round trip.  Results and bytes must be what a loop of the REFERENCE's zseek_pread gives
+    (short reads at frame boundaries, 0 at/after EOF, count 0); a consumer kernel queued on the same stream right
+    behind the call sees the data; a corrupt frame surfaces in batch_wait, not in the call."""
+    torch = torch_cuda
+    from datagen import refwriter, zsyn
+    data = zsyn.gen(5 << 20, seed=41) + b"z" * 12345
+    image = refwriter.write(data, codec, level, frame)
+    total = len(data)
+    rng = np.random.Generator(np.random.PCG64(18))
+    stream = torch.cuda.Stream()
+    with lib.Reader(image=image, cache_size=0) as rd, RefReader(image) as rr:
+        rd.load(0, rd.frames)
+        for rnd in range(3):
+            n = 3000
+            offs = rng.integers(0, total + 500, n).astype(np.uint64)
+            offs[:50] = (rd.d_off[rng.integers(1, rd.frames + 1, 50)].astype(np.int64) - rng.integers(1, 2000, 50)).astype(np.uint64)
+            counts = rng.choice([0, 1, 700, 4096], n).astype(np.uint64)
+            d_offs = torch.from_numpy(offs.astype(np.int64)).cuda()
+            d_counts = torch.from_numpy(counts.astype(np.int64)).cuda()
+            d_res = torch.full((n,), -7, dtype=torch.int64, device="cuda")
+            dst = torch.full((n * 4096,), 0x5A, dtype=torch.uint8, device="cuda")
+            with torch.cuda.stream(stream):
+                rd.pread_batch_async(d_offs, dst, dev_counts=d_counts if rnd != 1 else None, fixed_count=4096 if rnd == 1 else 0,
+                                     dst_stride=4096, dev_results=d_res, stream=stream if rnd != 2 else None)
+                if rnd == 2:
+                    rd.batch_wait()                       # the reader's own stream: wait before touching the results
+                checksum = dst.to(torch.int64).sum()      # consumer on the same stream, queued before any host wait
+            stream.synchronize()
+            rd.batch_wait()
+            res, out = d_res.cpu().numpy(), dst.cpu().numpy()
+            expect = np.full_like(out, 0x5A)
+            for i in range(n):
+                cnt = int(counts[i]) if rnd != 1 else 4096
+                r, b = rr.pread(cnt, int(offs[i]))
+                assert res[i] == r, (rnd, i)
+                expect[i * 4096:i * 4096 + r] = np.frombuffer(b, dtype=np.uint8)
+            assert (out == expect).all(), rnd
+            assert int(checksum.item()) == int(expect.astype(np.int64).sum())
+    # a corrupt frame: the call succeeds (nothing has run yet), batch_wait reports it
+    with OraclePort(image) as op:
+        c0, c1 = int(op.c_off[1]), int(op.c_off[2])
+    bad = bytearray(image)
+    for k in range(c0 + 12, c1, 5):
+        bad[k] ^= 0x3C
+    with lib.Reader(image=bytes(bad), cache_size=0) as rd:
+        rd.load(0, rd.frames)
+        d_offs = torch.from_numpy(rd.d_off[:3].astype(np.int64) + 100).cuda()
+        dst = torch.zeros(3 * 4096, dtype=torch.uint8, device="cuda")
+        rd.pread_batch_async(d_offs, dst, fixed_count=4096, dst_stride=4096)
+        with pytest.raises(lib.ZseekError) as e:
+            rd.batch_wait()
+        assert str(e.value).startswith("decompress frame")
+        assert dst[:4096].cpu().numpy().tobytes() == data[100:4196]          # the good frames of the batch are served
+
+
 @pytest.mark.parametrize("name", ["mix_lz4", "zsyn_zstd3_128k"])
 def test_eight_concurrent_callers_on_one_reader(lib, golden, name, torch_cuda):
     """zseek_pread and zseek_reader_stats may be called concurrently on one reader.  Eight threads
