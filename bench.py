@@ -497,8 +497,29 @@ def run_b200(args, rank, world):
             torch.cuda.synchronize()
             lat.append(time.perf_counter() - t0)
         lat.sort()
+        # the same cold 10,000-request batches through the stream-ordered API: request arrays resident in HBM, no host round trip
+        d_batches = [torch.from_numpy(gen_offsets(10000, rtotal, 4096, seed=100 + b).astype(np.int64)).cuda() for b in range(100)]
+        d_res = torch.zeros(10000, dtype=torch.int64, device="cuda")
+        rdc.pread_batch_async(d_batches[0], out, fixed_count=4096, dst_stride=4096, dev_results=d_res)
+        rdc.batch_wait()
+        alat = []
+        for b in range(100):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            rdc.pread_batch_async(d_batches[b], out, fixed_count=4096, dst_stride=4096, dev_results=d_res)
+            rdc.batch_wait()
+            alat.append(time.perf_counter() - t0)
+        alat.sort()
+        # check the last async batch completely against the writer's input
+        o10 = d_batches[99]
+        ends10 = torch.from_numpy(d_off[np.searchsorted(d_off, o10.cpu().numpy().astype(np.uint64), side="right")].astype(np.int64)).cuda()
+        want10 = torch.minimum(torch.full_like(o10, 4096), ends10 - o10)
+        exp = raw_dev[(o10[:, None] + ar[None, :]) % tile]
+        got = out[:10000 * 4096].view(10000, 4096)
+        async_ok = int((((exp == got) | (ar[None, :] >= want10[:, None])).all(dim=1) & (d_res == want10)).sum())
+        del d_batches
         results["random"] = dict(n=n_req, total=rtotal, frames=rdc.frames, cold_s=cold, warm_s=min(warm), p50_ms=lat[len(lat) // 2] * 1e3,
-                                 p99_ms=lat[98] * 1e3, short_reads=int((res < 4096).sum()), lengths_ok=len_ok, requests_ok=reqs_ok,
+                                 p99_ms=lat[98] * 1e3, async_p50_ms=alat[len(alat) // 2] * 1e3, async_p99_ms=alat[98] * 1e3, async_ok=async_ok, short_reads=int((res < 4096).sum()), lengths_ok=len_ok, requests_ok=reqs_ok,
                                  verified_bytes=bytes_ok, expected_bytes=int(want.sum()), C=int(rdc.c_off[-1]))
         rdc.close()
         del out, pinned
@@ -526,6 +547,14 @@ def run_b200(args, rank, world):
             cpu[name] = dict(gbps=round(med, 3), best=round(best, 3), gbps_1t=round(med1, 3), threads=threads, sample=sample)
             del image
 
+    dropin = None
+    if rank == 0 and world == 1 and args.dropin_mib > 0:
+        # the six-symbol drop-in path under the caller's own threads, both libraries, same C harness (tools/dropin_bench.py)
+        try:
+            p = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "dropin_bench.py"), str(args.dropin_mib)], capture_output=True, text=True, timeout=900)
+            dropin = json.loads(p.stdout.strip().splitlines()[-1]) if p.returncode == 0 else {"error": p.stderr[-300:]}
+        except Exception as e:  # noqa: BLE001
+            dropin = {"error": str(e)[:300]}
     if rank == 0:
         lz, zs = results["lz4"], results["zstd3"]
 
@@ -551,6 +580,8 @@ def run_b200(args, rank, world):
                                              "kind": "reference", "one_thread": cpu["zstd3"]["gbps_1t"]} if cpu else None)},
             "kernel_ms_lz4_sum": round(lz["kernel_ms"], 3),
         }
+        if dropin is not None:
+            extra["dropin_plain_zseek_pread"] = dropin
         if pcie:
             extra["pinned_copy_ceiling"] = {"h2d_GBps": round(pcie[0], 1), "d2h_GBps": round(pcie[1], 1),
                                             "e2e_lz4_fraction_of_d2h": round(lz["total"] * args.steps / lz["e2e_s"] / GB / pcie[1], 3),
@@ -580,7 +611,10 @@ def run_b200(args, rank, world):
                 "workload": f"BASELINE configs[3]: {rn['n']} x 4 KiB zseek_pread requests, uniform byte offsets, over a {rn['total'] >> 30} GiB zstd-3 "
                             f"file of {rn['frames']} frames (rank 0)",
                 "ops_per_s_cold": round(rn["n"] / rn["cold_s"]), "ops_per_s_warm_cache": round(rn["n"] / rn["warm_s"]),
-                "batch_10k_cold_p50_ms": round(rn["p50_ms"], 3), "batch_10k_cold_p99_ms": round(rn["p99_ms"], 3),
+                "batch_10k_cold_p50_ms": round(rn["async_p50_ms"], 3), "batch_10k_cold_p99_ms": round(rn["async_p99_ms"], 3),
+                "batch_10k_api": "zseek_b200_pread_batch_async, device-resident requests, call + zseek_b200_batch_wait timed on the host; "
+                                 f"last batch verified: {rn['async_ok']}/10000 requests",
+                "batch_10k_cold_p50_ms_host_arrays_lru_cache": round(rn["p50_ms"], 3), "batch_10k_cold_p99_ms_host_arrays_lru_cache": round(rn["p99_ms"], 3),
                 "short_reads_at_frame_boundaries": rn["short_reads"], "lengths_ok": rn["lengths_ok"], "requests_verified": rn["requests_ok"],
                 "verified_bytes": rn["verified_bytes"], "expected_bytes": rn["expected_bytes"],
                 "roofline_bound_ops_per_s": round(rn["n"] / ((rn["C"] + rn["total"] + 2 * rn["expected_bytes"]) / (peak * GB))),
@@ -688,6 +722,7 @@ def main():
     ap.add_argument("--random-ops", type=int, default=1000000)
     ap.add_argument("--random-gib", type=float, default=16.0, help="size of the zstd-3 file of the random-read leg (configs[3]: 16)")
     ap.add_argument("--c5-gib", type=float, default=8.0, help="per-GPU size of the configs[4] legs (0 = skip)")
+    ap.add_argument("--dropin-mib", type=int, default=512, help="file size of the plain-zseek_pread drop-in leg at N = 1 (0 = skip)")
     args = ap.parse_args()
     if args.tile_mib <= 0:
         args.tile_mib = int(args.size_gib * 1024)

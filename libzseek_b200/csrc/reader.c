@@ -125,6 +125,13 @@ struct zseek_reader {
     int async_stream;        /* ZSK_STREAM_COMPUTE or ZSK_STREAM_USER of the batch in flight; -1 = none */
     uint32_t async_jobs_max;
 
+    /* residency for random host readers: after resident_after isolated misses the whole shard is decoded once into the
+     * pinned window (if it is at most resident_max bytes); every later host read is a memcpy */
+    uint32_t random_misses, resident_after;
+    size_t resident_max;
+    bool resident_tried, resident;
+    size_t window_cap; /* bytes of one half of the ordinary read-ahead window (mirror_cap while not resident) */
+
     /* read-ahead */
     uint64_t ra_next;
     uint32_t ra_window, ra_max;
@@ -149,6 +156,7 @@ static void prefetch_drop(zseek_reader_t *r);
 static void prefetch_start(zseek_reader_t *r, void *call_data);
 static uint8_t *mirror_half(zseek_reader_t *r, int which);
 static size_t env_size(const char *name, size_t dflt);
+static bool stream_frames_to_host(zseek_reader_t *r, uint64_t lo, uint64_t hi, uint8_t *dst, void *call_data, char *errbuf);
 
 static void set_error(char errbuf[ZSEEK_ERRBUF_SIZE], const char *fmt, ...)
 {
@@ -644,6 +652,11 @@ static bool finish_decode(zseek_reader_t *r, uint32_t njobs, char *errbuf)
         return cuda_fail(r, errbuf, "decompress frame");
     for (uint32_t i = 0; i < njobs; i++)
         if (r->h_job_status[i] != ZSK_ST_OK) {
+            if (getenv("ZSEEK_B200_DEBUG")) {
+                uint32_t bad = 0;
+                for (uint32_t k = 0; k < njobs; k++) bad += r->h_job_status[k] != ZSK_ST_OK;
+                fprintf(stderr, "[zsk] job %u of %u failed with status %d (%u failed jobs in this launch)\n", i, njobs, r->h_job_status[i], bad);
+            }
             set_error(errbuf, "decompress frame: %s", status_name(r->h_job_status[i]));
             return false;
         }
@@ -829,6 +842,8 @@ static zseek_reader_t *reader_open_common(zseek_reader_t *r, size_t cache_size, 
         r->ra_max = (uint32_t)N;
     r->ra_window = 1;
     r->ra_next = UINT64_MAX;
+    r->resident_after = (uint32_t)env_size("ZSEEK_B200_RESIDENT_AFTER", 32);
+    r->resident_max = env_size("ZSEEK_B200_RESIDENT_MB", 4096) << 20;
     /* decoded-frame cache in HBM: what the caller asked for, and never fewer than 64 slots for device-side readers */
     r->nslots = (uint32_t)MAX(MAX(cache_size, 64), 1);
     if (N && r->nslots > N)
@@ -839,7 +854,7 @@ static zseek_reader_t *reader_open_common(zseek_reader_t *r, size_t cache_size, 
     r->stage_half = env_size("ZSEEK_B200_STAGE_MB", 64) * (1u << 20) / 2;
     if (r->stage_half < r->max_csize)
         r->stage_half = r->max_csize;
-    r->mirror_cap = (size_t)r->ra_max * r->max_dsize;
+    r->mirror_cap = r->window_cap = (size_t)r->ra_max * r->max_dsize;
     r->chunk_bytes = env_size("ZSEEK_B200_CHUNK_MB", 512) << 20;
     r->ramp_bytes = env_size("ZSEEK_B200_RAMP_MB", 16) << 20;
     r->sort_min = env_size("ZSEEK_B200_SORT_MIN", 40960);
@@ -943,6 +958,48 @@ bool zseek_reader_close(zseek_reader_t *reader, void *call_data, char errbuf[ZSE
 
 static bool stream_frames_to_host(zseek_reader_t *r, uint64_t lo, uint64_t hi, uint8_t *dst, void *call_data, char *errbuf);
 
+/* Decodes the whole shard into one pinned window; false (and the ordinary paths take over) when memory is short or a
+ * frame of the shard is bad. */
+static bool go_resident(zseek_reader_t *r, void *call_data)
+{
+    char scratch[ZSEEK_ERRBUF_SIZE];
+    const size_t bytes = (size_t)(r->d_off[r->shard_hi] - r->d_off[r->shard_lo]);
+    if (bytes == 0)
+        return false;
+    prefetch_drop(r);
+    zsk_cuda_stream_sync(r->cx, ZSK_STREAM_COMPUTE);
+    zsk_cuda_stream_sync(r->cx, ZSK_STREAM_D2H);
+    uint8_t *win = NULL;
+    if (zsk_cuda_malloc_host(r->cx, (void **)&win, bytes))
+        return false;
+    if (!stream_frames_to_host(r, r->shard_lo, r->shard_hi, win, call_data, scratch)) {
+        zsk_cuda_free_host(r->cx, win);
+        return false;
+    }
+    zsk_cuda_free_host(r->cx, r->h_mirror);
+    r->h_mirror = win; /* one half only: with the whole shard in the window no read-ahead is ever started */
+    r->mirror_cap = bytes;
+    r->mir_cur = 0;
+    r->mir_lo = r->shard_lo;
+    r->mir_hi = r->shard_hi;
+    r->resident = true;
+    return true;
+}
+
+/* back to the ordinary two-half read-ahead window (allocated again on first use) */
+static void drop_resident(zseek_reader_t *r)
+{
+    if (!r->resident)
+        return;
+    zsk_cuda_free_host(r->cx, r->h_mirror);
+    r->h_mirror = NULL;
+    r->mirror_cap = r->window_cap;
+    r->mir_lo = r->mir_hi = 0;
+    r->mir_cur = 0;
+    r->resident = r->resident_tried = false;
+    r->random_misses = 0;
+}
+
 /* ------------------------------------------------------------------ zseek_pread (reference src/decompress.c:806-824) */
 static ssize_t pread_locked(zseek_reader_t *r, void *buf, size_t count, size_t offset, void *call_data, char *errbuf)
 {
@@ -987,6 +1044,16 @@ static ssize_t pread_locked(zseek_reader_t *r, void *buf, size_t count, size_t o
             r->ra_window = MIN(r->ra_window * 4, r->ra_max);
         else
             r->ra_window = 1;
+        if (!on_device && r->ra_window == 1 && !r->resident_tried && r->resident_after && ++r->random_misses >= r->resident_after &&
+            r->d_off[r->shard_hi] - r->d_off[r->shard_lo] <= r->resident_max) {
+            /* a host reader that keeps missing at random places: decode the whole shard once (every frame is going to be
+             * wanted sooner or later, and one launch over thousands of frames is what the GPU is good at) */
+            r->resident_tried = true;
+            if (go_resident(r, call_data)) {
+                memcpy(buf, mirror_half(r, r->mir_cur) + (offset - r->d_off[r->mir_lo]), n);
+                return (ssize_t)n;
+            }
+        }
         if (!on_device && !ensure_mirror(r, errbuf))
             return -1;
         uint64_t hi = MIN(f + (on_device ? MIN(r->ra_window, r->nslots) : r->ra_window), r->shard_hi);
@@ -1089,6 +1156,7 @@ bool zseek_b200_set_shard(zseek_reader_t *r, unsigned rank, unsigned world, char
     }
     pthread_mutex_lock(&r->lock);
     prefetch_drop(r);
+    drop_resident(r);
     r->shard_lo = r->nframes * rank / world;
     r->shard_hi = r->nframes * (rank + 1) / world;
     pthread_mutex_unlock(&r->lock);
@@ -1813,6 +1881,7 @@ void zseek_b200_cache_clear(zseek_reader_t *r)
         return;
     pthread_mutex_lock(&r->lock);
     prefetch_drop(r);
+    drop_resident(r);
     cache_clear(r);
     pthread_mutex_unlock(&r->lock);
 }

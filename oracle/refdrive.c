@@ -273,7 +273,11 @@ typedef struct {
     size_t bytes; size_t ops; int err;
     pthread_barrier_t *bar;
     double t_start, t_end;
+    void *shared_rd; /* refdrive_set_shared(1): every thread calls into this one reader instead of opening its own */
 } job_t;
+
+static int G_shared;
+EXPORT void refdrive_set_shared(int on) { G_shared = on; }
 
 static void pin_to(int cpu)
 {
@@ -291,7 +295,7 @@ static void *scan_thread(void *arg)
         pin_to(j->tid % (int)sysconf(_SC_NPROCESSORS_ONLN));
     memimg_t img = { j->image, j->size };
     zseek_read_file_t uf = { &img, memimg_pread, memimg_fsize };
-    void *rd = R.reader_open_full(uf, j->cache_size, NULL, errbuf);
+    void *rd = j->shared_rd ? j->shared_rd : R.reader_open_full(uf, j->cache_size, NULL, errbuf);
     uint8_t *scratch = j->dst ? NULL : malloc(j->req);
     if (!rd || (!j->dst && !scratch)) {
         j->err = 1;
@@ -317,7 +321,8 @@ static void *scan_thread(void *arg)
         j->bytes += got;
     }
     j->t_end = now_s();
-    R.reader_close(rd, NULL, errbuf);
+    if (!j->shared_rd)
+        R.reader_close(rd, NULL, errbuf);
     free(scratch);
     return NULL;
 }
@@ -335,8 +340,15 @@ EXPORT double refdrive_scan(const void *image, size_t size, size_t dsize, int th
     pthread_t *th = calloc((size_t)threads, sizeof(pthread_t));
     pthread_barrier_t bar;
     pthread_barrier_init(&bar, NULL, (unsigned)threads);
+    char serr[ZSEEK_ERRBUF_SIZE];
+    memimg_t simg = { image, size };
+    zseek_read_file_t suf = { &simg, memimg_pread, memimg_fsize };
+    void *shared = G_shared ? R.reader_open_full(suf, cache_size, NULL, serr) : NULL;
+    if (G_shared && !shared)
+        return -9.0;
     for (int t = 0; t < threads; t++) {
         job_t *j = &jobs[t];
+        j->shared_rd = shared;
         j->image = image; j->size = size; j->tid = t; j->threads = threads; j->pin = pin;
         j->cache_size = cache_size; j->req = req; j->dst = dst; j->bar = &bar;
         j->lo = (size_t)((unsigned __int128)dsize * (unsigned)t / (unsigned)threads);
@@ -355,6 +367,7 @@ EXPORT double refdrive_scan(const void *image, size_t size, size_t dsize, int th
     }
     pthread_barrier_destroy(&bar);
     free(jobs); free(th);
+    if (shared) R.reader_close(shared, NULL, serr);
     if (bytes_out) *bytes_out = bytes;
     return err ? -(double)err : t1 - t0;
 }
@@ -367,7 +380,7 @@ static void *random_thread(void *arg)
         pin_to(j->tid % (int)sysconf(_SC_NPROCESSORS_ONLN));
     memimg_t img = { j->image, j->size };
     zseek_read_file_t uf = { &img, memimg_pread, memimg_fsize };
-    void *rd = R.reader_open_full(uf, j->cache_size, NULL, errbuf);
+    void *rd = j->shared_rd ? j->shared_rd : R.reader_open_full(uf, j->cache_size, NULL, errbuf);
     uint8_t *scratch = malloc(j->count ? j->count : 1);
     if (!rd || !scratch) {
         j->err = 1;
@@ -392,7 +405,8 @@ static void *random_thread(void *arg)
         j->ops++;
     }
     j->t_end = now_s();
-    R.reader_close(rd, NULL, errbuf);
+    if (!j->shared_rd)
+        R.reader_close(rd, NULL, errbuf);
     free(scratch);
     return NULL;
 }
@@ -408,8 +422,15 @@ EXPORT double refdrive_random(const void *image, size_t size, const uint64_t *of
     pthread_t *th = calloc((size_t)threads, sizeof(pthread_t));
     pthread_barrier_t bar;
     pthread_barrier_init(&bar, NULL, (unsigned)threads);
+    char serr[ZSEEK_ERRBUF_SIZE];
+    memimg_t simg = { image, size };
+    zseek_read_file_t suf = { &simg, memimg_pread, memimg_fsize };
+    void *shared = G_shared ? R.reader_open_full(suf, cache_size, NULL, serr) : NULL;
+    if (G_shared && !shared)
+        return -9.0;
     for (int t = 0; t < threads; t++) {
         job_t *j = &jobs[t];
+        j->shared_rd = shared;
         j->image = image; j->size = size; j->tid = t; j->threads = threads; j->pin = pin;
         j->cache_size = cache_size; j->offsets = offsets; j->count = count; j->dst = dst; j->bar = &bar;
         j->n_lo = n * (size_t)t / (size_t)threads;
@@ -428,6 +449,7 @@ EXPORT double refdrive_random(const void *image, size_t size, const uint64_t *of
     }
     pthread_barrier_destroy(&bar);
     free(jobs); free(th);
+    if (shared) R.reader_close(shared, NULL, serr);
     if (ops_out) *ops_out = ops;
     return err ? -(double)err : t1 - t0;
 }

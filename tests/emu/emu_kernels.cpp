@@ -60,7 +60,7 @@ void emu_decode(int codec, const uint8_t *comp, uint64_t comp_base, const uint64
 {
     uint32_t counter = 0;
     std::vector<uint8_t> scratch((size_t)ctas * ZSK_LIT_SCRATCH + 64);
-    zsk_decode_args a;
+    zsk_decode_args a{};
     a.c_off = c_off; a.d_off = d_off; a.comp = comp; a.comp_base = comp_base; a.frame_ids = frame_ids;
     a.dst_offs = dst_offs; a.dst = dst; a.dst_base = dst_base; a.first_frame = first_frame; a.njobs = njobs;
     a.status = status; a.work_counter = &counter; a.scratch = scratch.data(); a.limits = limits;
