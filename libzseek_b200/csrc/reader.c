@@ -13,7 +13,7 @@
  *   src/cache.c               LRU of malloc'd frames        -> HBM slab of nslots decoded frames with a real
  *                                                             O(1) LRU (the reference list is buggy)
  *   src/buffer.c              growable staging buffers      -> pinned ingest staging (h_stage) + pinned decoded
- *                                                             window mirror (h_mirror) + device compressed image
+ *                                                             windows (h_mir[]) + device compressed image
  *   src/common.c              set_error                     -> set_error (same message strings)
  */
 #define _GNU_SOURCE
@@ -74,8 +74,8 @@ struct zseek_reader {
     uint8_t *h_stage; /* two halves */
     size_t stage_half;
     int stage_next, stage_inflight;
-    uint8_t *h_mirror; /* two halves of mirror_cap bytes; half mir_cur holds the decoded bytes of frames [mir_lo, mir_hi) */
-    size_t mirror_cap;
+    uint8_t *h_mir[2]; /* two pinned windows of mir_cap[] bytes; window mir_cur holds the decoded bytes of frames [mir_lo, mir_hi) */
+    size_t mir_cap[2];
     uint64_t mir_lo, mir_hi;
     int mir_cur;
     /* asynchronous read-ahead of a sequential host scan: frames [pf_lo, pf_hi) are being decoded into the OTHER half
@@ -130,7 +130,7 @@ struct zseek_reader {
     uint32_t random_misses, resident_after;
     size_t resident_max;
     bool resident_tried, resident;
-    size_t window_cap; /* bytes of one half of the ordinary read-ahead window (mirror_cap while not resident) */
+    size_t window_cap; /* most bytes an ordinary read-ahead window holds */
 
     /* read-ahead */
     uint64_t ra_next;
@@ -515,12 +515,20 @@ static bool ensure_stage(zseek_reader_t *r, char *errbuf)
     return true;
 }
 
-static bool ensure_mirror(zseek_reader_t *r, char *errbuf)
+/* pinned window `which` of at least `bytes` (grown geometrically up to window_cap: a reader that only ever sees small
+ * windows never pins the 2 x 128 MiB of the largest one).  The window must not be the one reads are served from. */
+static bool ensure_window(zseek_reader_t *r, int which, size_t bytes, char *errbuf)
 {
-    if (r->h_mirror)
+    if (r->h_mir[which] && bytes <= r->mir_cap[which])
         return true;
-    if (zsk_cuda_malloc_host(r->cx, (void **)&r->h_mirror, 2 * r->mirror_cap))
+    zsk_cuda_stream_sync(r->cx, ZSK_STREAM_D2H);
+    size_t cap = MAX(bytes, MIN(r->window_cap, MAX(2 * r->mir_cap[which], (size_t)4 << 20)));
+    zsk_cuda_free_host(r->cx, r->h_mir[which]);
+    r->h_mir[which] = NULL;
+    r->mir_cap[which] = 0;
+    if (zsk_cuda_malloc_host(r->cx, (void **)&r->h_mir[which], cap))
         return cuda_fail(r, errbuf, "allocate pinned window");
+    r->mir_cap[which] = cap;
     return true;
 }
 
@@ -777,7 +785,7 @@ static void reader_free(zseek_reader_t *r)
                         r->g_out, r->g_bslab, r->g_bjob_ids, r->g_bjob_limits, r->g_bctl, r->g_bjob_offs, r->g_bjob_status, r->g_bsrc };
         for (size_t i = 0; i < sizeof(dev) / sizeof(dev[0]); i++)
             zsk_cuda_free(r->cx, dev[i]);
-        void *pin[] = { r->h_stage, r->h_mirror, r->h_job_ids, r->h_job_offs, r->h_job_status, r->h_job_limits };
+        void *pin[] = { r->h_stage, r->h_mir[0], r->h_mir[1], r->h_job_ids, r->h_job_offs, r->h_job_status, r->h_job_limits };
         for (size_t i = 0; i < sizeof(pin) / sizeof(pin[0]); i++)
             zsk_cuda_free_host(r->cx, pin[i]);
         zsk_cuda_ctx_destroy(r->cx);
@@ -854,7 +862,7 @@ static zseek_reader_t *reader_open_common(zseek_reader_t *r, size_t cache_size, 
     r->stage_half = env_size("ZSEEK_B200_STAGE_MB", 64) * (1u << 20) / 2;
     if (r->stage_half < r->max_csize)
         r->stage_half = r->max_csize;
-    r->mirror_cap = r->window_cap = (size_t)r->ra_max * r->max_dsize;
+    r->window_cap = (size_t)r->ra_max * r->max_dsize;
     r->chunk_bytes = env_size("ZSEEK_B200_CHUNK_MB", 512) << 20;
     r->ramp_bytes = env_size("ZSEEK_B200_RAMP_MB", 16) << 20;
     r->sort_min = env_size("ZSEEK_B200_SORT_MIN", 40960);
@@ -887,7 +895,7 @@ static zseek_reader_t *reader_open_common(zseek_reader_t *r, size_t cache_size, 
         zsk_cuda_malloc(r->cx, (void **)&r->g_doff, (N + 1) * sizeof(uint64_t)) ||
         zsk_cuda_malloc(r->cx, (void **)&r->g_frame_src, (N + 1) * sizeof(int64_t)) ||
         zsk_cuda_malloc(r->cx, (void **)&r->g_slab, (size_t)r->nslots * r->slot_size + ZSK_PAD_FRONT + ZSK_PAD_BACK)) {
-        /* the pinned ingest staging (h_stage) and the pinned decoded window (h_mirror) are allocated on first use:
+        /* the pinned ingest staging (h_stage) and the pinned decoded windows (h_mir[]) are allocated on first use:
          * readers that only serve device buffers or batches never pay for them */
         set_error(errbuf, "buffer creation failed: %s", zsk_cuda_error(r->cx));
         goto fail;
@@ -976,9 +984,12 @@ static bool go_resident(zseek_reader_t *r, void *call_data)
         zsk_cuda_free_host(r->cx, win);
         return false;
     }
-    zsk_cuda_free_host(r->cx, r->h_mirror);
-    r->h_mirror = win; /* one half only: with the whole shard in the window no read-ahead is ever started */
-    r->mirror_cap = bytes;
+    zsk_cuda_free_host(r->cx, r->h_mir[0]);
+    zsk_cuda_free_host(r->cx, r->h_mir[1]);
+    r->h_mir[0] = win; /* with the whole shard in the window no read-ahead is ever started */
+    r->h_mir[1] = NULL;
+    r->mir_cap[0] = bytes;
+    r->mir_cap[1] = 0;
     r->mir_cur = 0;
     r->mir_lo = r->shard_lo;
     r->mir_hi = r->shard_hi;
@@ -991,9 +1002,9 @@ static void drop_resident(zseek_reader_t *r)
 {
     if (!r->resident)
         return;
-    zsk_cuda_free_host(r->cx, r->h_mirror);
-    r->h_mirror = NULL;
-    r->mirror_cap = r->window_cap;
+    zsk_cuda_free_host(r->cx, r->h_mir[0]);
+    r->h_mir[0] = NULL;
+    r->mir_cap[0] = 0;
     r->mir_lo = r->mir_hi = 0;
     r->mir_cur = 0;
     r->resident = r->resident_tried = false;
@@ -1041,7 +1052,7 @@ static ssize_t pread_locked(zseek_reader_t *r, void *buf, size_t count, size_t o
         /* miss: decode a window of frames in one launch; the window grows while the access pattern
          * stays sequential and collapses to a single frame on a random access */
         if (f == r->ra_next)
-            r->ra_window = MIN(r->ra_window * 4, r->ra_max);
+            r->ra_window = MIN(r->ra_window * 8, r->ra_max); /* a launch costs ~10 ms whatever its size: grow fast */
         else
             r->ra_window = 1;
         if (!on_device && r->ra_window == 1 && !r->resident_tried && r->resident_after && ++r->random_misses >= r->resident_after &&
@@ -1054,9 +1065,12 @@ static ssize_t pread_locked(zseek_reader_t *r, void *buf, size_t count, size_t o
                 return (ssize_t)n;
             }
         }
-        if (!on_device && !ensure_mirror(r, errbuf))
-            return -1;
         uint64_t hi = MIN(f + (on_device ? MIN(r->ra_window, r->nslots) : r->ra_window), r->shard_hi);
+        if (!on_device) { /* the window reads are served from is about to be replaced anyway */
+            r->mir_lo = r->mir_hi = 0;
+            if (!ensure_window(r, r->mir_cur, (size_t)(r->d_off[hi] - r->d_off[f]), errbuf))
+                return -1;
+        }
         bool ok;
         if (!on_device && hi - f > 1) {
             /* sequential host reader: decode the window through the H2D / decode / D2H pipeline straight into
@@ -1142,7 +1156,7 @@ bool zseek_reader_stats(zseek_reader_t *reader, zseek_reader_stats_t *stats, cha
     stats->decompressed_size = (size_t)reader->d_off[reader->nframes];
     stats->cache_memory = (size_t)reader->cached * reader->slot_size;
     stats->cached_frames = reader->cached;
-    stats->buffer_size = reader->g_comp_cap + (reader->h_stage ? 2 * reader->stage_half : 0) + (reader->h_mirror ? 2 * reader->mirror_cap : 0);
+    stats->buffer_size = reader->g_comp_cap + (reader->h_stage ? 2 * reader->stage_half : 0) + reader->mir_cap[0] + reader->mir_cap[1];
     pthread_mutex_unlock(&reader->lock);
     return true;
 }
@@ -1464,7 +1478,7 @@ static bool stream_frames_to_host(zseek_reader_t *r, uint64_t lo, uint64_t hi, u
 }
 
 /* ---- asynchronous read-ahead of the plain zseek_pread path */
-static uint8_t *mirror_half(zseek_reader_t *r, int which) { return r->h_mirror + (size_t)which * r->mirror_cap; }
+static uint8_t *mirror_half(zseek_reader_t *r, int which) { return r->h_mir[which]; }
 
 /* Waits for the queued read-ahead (if any) and forgets it: every path that uses the streams, the staging buffers or the
  * job buffers calls this first. */
@@ -1482,9 +1496,11 @@ static void prefetch_start(zseek_reader_t *r, void *call_data)
 {
     if (r->pf_active || r->mir_hi <= r->mir_lo || r->mir_hi >= r->shard_hi || r->mir_hi - r->mir_lo < 4)
         return;
-    r->ra_window = MIN(r->ra_window * 4, r->ra_max);
+    r->ra_window = MIN(r->ra_window * 8, r->ra_max);
     uint64_t lo = r->mir_hi, hi = MIN(lo + r->ra_window, r->shard_hi);
     char scratch[ZSEEK_ERRBUF_SIZE]; /* a failing read-ahead is not an error of this call: the window is retried synchronously */
+    if (!ensure_window(r, r->mir_cur ^ 1, (size_t)(r->d_off[hi] - r->d_off[lo]), scratch))
+        return;
     r->pf_ok = stream_frames_begin(r, lo, hi, mirror_half(r, r->mir_cur ^ 1), call_data, scratch, &r->pf_resident);
     r->pf_lo = lo;
     r->pf_hi = hi;

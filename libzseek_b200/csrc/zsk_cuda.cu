@@ -385,9 +385,17 @@ static int launch_zstd_pipeline(zsk_cuda_ctx *cx, zsk_decode_args a, cudaStream_
     z.deferred = cx->zdeferred;
     z.bprog = cx->zbprog;
     CK(cx, cudaMemsetAsync(z.ctr, 0, ZSK_ZC_N * sizeof(unsigned long long), s));
+    /* grids follow the work of the launch (an estimate: one block per 32 KiB of output), so that the small launches of
+     * several readers run side by side instead of each filling the GPU with CTAs that find nothing to do */
+    const size_t est_blocks = (size_t)(dsum >> 15) + njobs;
+    const size_t fse_units = a.limits ? njobs : est_blocks; /* with limits a trio owns a frame, else a block */
+    unsigned fse_ctas = (unsigned)((fse_units + ZSK_ZFSE_WARPS * ZSK_ZFSE_TRIOS - 1) / (ZSK_ZFSE_WARPS * ZSK_ZFSE_TRIOS));
+    if (fse_ctas > (unsigned)cx->zfse_ctas) fse_ctas = (unsigned)cx->zfse_ctas;
+    unsigned huf_ctas = (unsigned)((est_blocks + ZSK_ZHUF_SLOTS - 1) / ZSK_ZHUF_SLOTS);
+    if (huf_ctas > (unsigned)cx->zhuf_ctas) huf_ctas = (unsigned)cx->zhuf_ctas;
     zsk_zstd_index_kernel<<<(unsigned)((njobs + 127) / 128), 128, 0, s>>>(z);
-    zsk_zstd_fse_kernel<<<cx->zfse_ctas, ZSK_ZFSE_THREADS, ZSK_ZFSE_SMEM, s>>>(z);
-    zsk_zstd_huf_kernel<<<cx->zhuf_ctas, 32, ZSK_ZHUF_SMEM, s>>>(z);
+    zsk_zstd_fse_kernel<<<fse_ctas, ZSK_ZFSE_THREADS, ZSK_ZFSE_SMEM, s>>>(z);
+    zsk_zstd_huf_kernel<<<huf_ctas, 32, ZSK_ZHUF_SMEM, s>>>(z);
     unsigned xctas = njobs < (size_t)cx->zexec_ctas ? (unsigned)njobs : (unsigned)cx->zexec_ctas;
     zsk_zstd_exec_kernel<<<xctas, 32, ZSK_ZX_SMEM, s>>>(z);
     /* frames P0 / P1a handed over (normally none: the CTAs find an empty list and leave) */

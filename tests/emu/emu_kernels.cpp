@@ -50,6 +50,7 @@ static void emu_zstd_pipeline(zsk_decode_args a, uint32_t njobs, uint32_t ctas, 
 
 extern "C" {
 __attribute__((visibility("default"))) uint32_t emu_last_deferred() { return g_emu_deferred; }
+__attribute__((visibility("default"))) void emu_set_addr_bias(uint32_t bias) { zsk_emu_addr_bias = bias & ~15u; }
 
 /* comp points at the byte with file offset comp_base; the caller guarantees >= 16 readable bytes
  * before it and >= 64 after the last frame (same contract as the device buffers). */

@@ -21,10 +21,11 @@ def lib():
     L.emu_gather.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                              C.c_uint64, C.c_uint32]
     L.emu_last_deferred.restype = C.c_uint32
+    L.emu_set_addr_bias.argtypes = [C.c_uint32]
     return L
 
 
-def decode_all(L, image: bytes, codec: int, c_off: np.ndarray, d_off: np.ndarray, ctas: int = 3, misalign: int = 0, limits=None):
+def decode_all(L, image: bytes, codec: int, c_off: np.ndarray, d_off: np.ndarray, ctas: int = 3, misalign: int = 0, limits=None, wrap_at=None):
     """Whole-file decode with the emulated K2/K3; returns (decoded bytes, status array)."""
     n = len(c_off) - 1
     payload = int(c_off[-1])
@@ -37,8 +38,11 @@ def decode_all(L, image: bytes, codec: int, c_off: np.ndarray, d_off: np.ndarray
     status = np.full(max(n, 1), -1, dtype=np.int32)
     c_off = np.ascontiguousarray(c_off, dtype=np.uint64)
     d_off = np.ascontiguousarray(d_off, dtype=np.uint64)
+    if wrap_at is not None:   # low 32 address bits wrap around `wrap_at` bytes into the compressed image
+        L.emu_set_addr_bias((-(comp.ctypes.data + FRONT_PAD + wrap_at)) & 0xFFFFFFF0)
     L.emu_decode(codec, comp.ctypes.data + FRONT_PAD, 0, c_off.ctypes.data, d_off.ctypes.data, None, None,
                  dst.ctypes.data, 0, 0, n, status.ctypes.data, ctas, limits.ctypes.data if limits is not None else None)
+    L.emu_set_addr_bias(0)
     assert (dst[total:] == 0xEE).all(), "emulated kernel wrote past the end of the output"
     assert (raw[:lead] == 0xEE).all(), "emulated kernel wrote before the start of the output"
     return dst[:total], status[:n]

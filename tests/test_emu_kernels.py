@@ -47,6 +47,21 @@ def test_emulated_zstd_deferred_frames(emu, golden, name, kernel):
     assert hashlib.sha256(out.tobytes()).hexdigest() == c["input_sha256"]
 
 
+@pytest.mark.parametrize("name", ["zsyn_zstd3_128k", "mix_zstd19"])
+def test_emulated_zstd_bitstream_ring_across_a_4gib_address_boundary(emu, golden, name):
+    """The FSE stage stages each block's bitstream in a shared-memory ring addressed by the LOW 32 bits of the global address.
+    A compressed image of a few GiB straddles a 4 GiB boundary somewhere, where those bits wrap (seen on the B200: one
+    frame of 16,384 failed).  The emulator moves the wrap to many places inside the image."""
+    cases, _ = golden
+    c = cases[name]
+    with OraclePort(c["image"]) as op:
+        payload = int(op.c_off[-1])
+        for wrap_at in list(range(16, payload, max(16, payload // 23))) + [payload - 7]:
+            out, status = emu_api.decode_all(emu, c["image"], op.codec, op.c_off, op.d_off, ctas=2, wrap_at=wrap_at)
+            assert (status == 0).all(), (wrap_at, status)
+            assert hashlib.sha256(out.tobytes()).hexdigest() == c["input_sha256"], wrap_at
+
+
 @pytest.mark.parametrize("misalign", [1, 7, 15, 17, 31])
 @pytest.mark.parametrize("name", ["zsyn_zstd3_128k", "mix_zstd19"])
 def test_emulated_zstd_pipeline_unaligned_output(emu, golden, name, misalign):
