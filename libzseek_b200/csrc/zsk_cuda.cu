@@ -5,6 +5,7 @@
  * zsk_cuda_ctx_create fails and zseek_reader_open* reports the error.
  */
 #include <cuda_runtime.h>
+#include <pthread.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -20,6 +21,7 @@
 struct zsk_cuda_ctx {
     int device;
     int sm_count;
+    cudaStream_t alloc_stream;            /* cudaMallocAsync / cudaFreeAsync */
     cudaStream_t streams[ZSK_NSTREAMS + 1];   /* + ZSK_STREAM_USER: caller-owned, never created or destroyed here */
     cudaEvent_t sync_ev;                 /* cross-stream dependencies */
     cudaEvent_t user_ev[ZSK_NEVENTS];
@@ -110,13 +112,20 @@ int zsk_cuda_ctx_create(int device, zsk_cuda_ctx **out, char *err, size_t errlen
     }
     cx->sm_count = prop.multiProcessorCount;
     for (int i = 0; i < ZSK_NSTREAMS; i++) CK0(cudaStreamCreateWithFlags(&cx->streams[i], cudaStreamNonBlocking));
+    CK0(cudaStreamCreateWithFlags(&cx->alloc_stream, cudaStreamNonBlocking));
+    {
+        cudaMemPool_t pool;
+        CK0(cudaDeviceGetDefaultMemPool(&pool, device));
+        unsigned long long keep = ~0ull; /* freed buffers stay in the pool */
+        CK0(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    }
     CK0(cudaEventCreateWithFlags(&cx->sync_ev, cudaEventDisableTiming));
     for (int i = 0; i < ZSK_NEVENTS; i++) CK0(cudaEventCreateWithFlags(&cx->user_ev[i], cudaEventDisableTiming));
     CK0(cudaEventCreate(&cx->t0));
     CK0(cudaEventCreate(&cx->t1));
     CK0(cudaEventCreate(&cx->k0));
     CK0(cudaEventCreate(&cx->k1));
-    CK0(cudaMalloc((void **)&cx->counters, ZSK_NCOUNTERS * sizeof(uint32_t)));
+    CK0(cudaMallocAsync((void **)&cx->counters, ZSK_NCOUNTERS * sizeof(uint32_t), cx->alloc_stream));
     int per_sm = 0;
     CK0(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, zsk_zstd_decode_kernel, ZSK_ZSTD_CTA_THREADS, 0));
     if (per_sm < 1) per_sm = 1;
@@ -146,7 +155,8 @@ int zsk_cuda_ctx_create(int device, zsk_cuda_ctx **out, char *err, size_t errlen
         if (v >= 1 && v < per_sm) per_sm = v;
     }
     cx->zexec_ctas = (per_sm < 1 ? 1 : per_sm) * cx->sm_count;
-    CK0(cudaMalloc((void **)&cx->zctr, ZSK_NCOUNTERS * ZSK_ZC_N * sizeof(unsigned long long)));
+    CK0(cudaMallocAsync((void **)&cx->zctr, ZSK_NCOUNTERS * ZSK_ZC_N * sizeof(unsigned long long), cx->alloc_stream));
+    CK0(cudaStreamSynchronize(cx->alloc_stream));
     CK0(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, zsk_lz4_decode_batch_kernel, ZSK_LZ4_CTA_THREADS, 0));
     if (per_sm < 1) per_sm = 1;
     if (const char *g = getenv("ZSEEK_B200_LZ4_CTAS_PER_SM")) { /* tuning knob: resident LZ4 CTAs per SM */
@@ -189,9 +199,11 @@ void zsk_cuda_ctx_destroy(zsk_cuda_ctx *cx)
     cudaEventDestroy(cx->t1);
     cudaEventDestroy(cx->k0);
     cudaEventDestroy(cx->k1);
-    cudaFree(cx->counters);
-    cudaFree(cx->scratch);
-    cudaFree(cx->zbprog); cudaFree(cx->zframes); cudaFree(cx->zdeferred); cudaFree(cx->zblocks); cudaFree(cx->zseqs); cudaFree(cx->zlits); cudaFree(cx->zctr);
+    void *pools[] = { cx->counters, cx->scratch, cx->zctr, cx->zbprog, cx->zframes, cx->zdeferred, cx->zblocks, cx->zseqs, cx->zlits };
+    for (size_t i = 0; i < sizeof(pools) / sizeof(pools[0]); i++)
+        if (pools[i]) cudaFreeAsync(pools[i], cx->alloc_stream);
+    cudaStreamSynchronize(cx->alloc_stream);
+    cudaStreamDestroy(cx->alloc_stream);
     free(cx);
 }
 
@@ -229,10 +241,18 @@ size_t zsk_cuda_free_memory(zsk_cuda_ctx *cx)
     return fr;
 }
 
+/*
+ * Device memory comes from the device's default stream-ordered pool (cudaMallocAsync) with the release threshold
+ * lifted: a freed buffer goes back to the pool instead of the driver, and neither call synchronises the DEVICE the way
+ * cudaFree does — with one reader per caller thread, sixteen readers growing their windows used to stop each other's
+ * kernels hundreds of times per scan.  The allocation is made usable from every stream of the context by waiting for
+ * the (otherwise idle) allocation stream; callers free a buffer only after the streams that used it were waited for.
+ */
 int zsk_cuda_malloc(zsk_cuda_ctx *cx, void **p, size_t n)
 {
     CK(cx, cudaSetDevice(cx->device));
-    CK(cx, cudaMalloc(p, n ? n : 1));
+    CK(cx, cudaMallocAsync(p, n ? n : 1, cx->alloc_stream));
+    CK(cx, cudaStreamSynchronize(cx->alloc_stream));
     return 0;
 }
 
@@ -240,21 +260,67 @@ int zsk_cuda_free(zsk_cuda_ctx *cx, void *p)
 {
     if (!p) return 0;
     CK(cx, cudaSetDevice(cx->device));
-    CK(cx, cudaFree(p));
+    CK(cx, cudaFreeAsync(p, cx->alloc_stream));
     return 0;
+}
+
+/*
+ * Pinned host memory is expensive to create (page pinning under a process-wide driver lock), and readers come and go:
+ * buffers are rounded up to a power of two and recycled through a small process-wide free list (at most
+ * ZSK_PIN_CACHE_BYTES stay cached).
+ */
+#define ZSK_PIN_CLASSES 40
+#define ZSK_PIN_CACHE_BYTES ((size_t)2 << 30)
+#define ZSK_PIN_HDR 64
+struct zsk_pin_node { zsk_pin_node *next; };
+static pthread_mutex_t g_pin_mu = PTHREAD_MUTEX_INITIALIZER;
+static zsk_pin_node *g_pin_free[ZSK_PIN_CLASSES];
+static size_t g_pin_cached;
+
+static int pin_class(size_t n)
+{
+    int c = 12; /* 4 KiB */
+    while (c < ZSK_PIN_CLASSES - 1 && ((size_t)1 << c) < n) c++;
+    return c;
 }
 
 int zsk_cuda_malloc_host(zsk_cuda_ctx *cx, void **p, size_t n)
 {
-    CK(cx, cudaSetDevice(cx->device));
-    CK(cx, cudaHostAlloc(p, n ? n : 1, cudaHostAllocDefault));
+    const int c = pin_class(n + ZSK_PIN_HDR);
+    const size_t bytes = (size_t)1 << c;
+    pthread_mutex_lock(&g_pin_mu);
+    zsk_pin_node *nd = g_pin_free[c];
+    if (nd) {
+        g_pin_free[c] = nd->next;
+        g_pin_cached -= bytes;
+    }
+    pthread_mutex_unlock(&g_pin_mu);
+    if (!nd) {
+        CK(cx, cudaSetDevice(cx->device));
+        void *raw = NULL;
+        CK(cx, cudaHostAlloc(&raw, bytes, cudaHostAllocPortable));
+        nd = (zsk_pin_node *)raw;
+    }
+    *(int *)((char *)nd + 8) = c; /* the class lives in the header in front of the caller's bytes */
+    *p = (char *)nd + ZSK_PIN_HDR;
     return 0;
 }
 
 int zsk_cuda_free_host(zsk_cuda_ctx *cx, void *p)
 {
     if (!p) return 0;
-    CK(cx, cudaFreeHost(p));
+    zsk_pin_node *nd = (zsk_pin_node *)((char *)p - ZSK_PIN_HDR);
+    const int c = *(int *)((char *)nd + 8);
+    const size_t bytes = (size_t)1 << c;
+    pthread_mutex_lock(&g_pin_mu);
+    const bool keep = g_pin_cached + bytes <= ZSK_PIN_CACHE_BYTES;
+    if (keep) {
+        nd->next = g_pin_free[c];
+        g_pin_free[c] = nd;
+        g_pin_cached += bytes;
+    }
+    pthread_mutex_unlock(&g_pin_mu);
+    if (!keep) CK(cx, cudaFreeHost(nd));
     return 0;
 }
 
@@ -328,19 +394,23 @@ static int next_counter(zsk_cuda_ctx *cx, int stream, uint32_t **out)
     return 0;
 }
 
-/* (re)allocates *p to hold `need` bytes; growth is geometric.  cudaFree waits for everything in flight on the device. */
+/* (re)allocates *p to hold `need` bytes; growth is geometric */
 static int grow_pool(zsk_cuda_ctx *cx, void **p, size_t *cap_bytes, size_t need)
 {
     if (need <= *cap_bytes) return 0;
     size_t want = need > 2 * *cap_bytes ? need : 2 * *cap_bytes;
-    if (*p) CK(cx, cudaFree(*p));
+    /* the pools are shared by every launch of this context: the launches in flight must be through with them */
+    for (int i = 0; i < ZSK_NSTREAMS; i++) CK(cx, cudaStreamSynchronize(cx->streams[i]));
+    if (cx->streams[ZSK_STREAM_USER]) CK(cx, cudaStreamSynchronize(cx->streams[ZSK_STREAM_USER]));
+    if (*p) CK(cx, cudaFreeAsync(*p, cx->alloc_stream));
     *p = NULL;
     *cap_bytes = 0;
-    if (cudaMalloc(p, want) != cudaSuccess) {
+    if (cudaMallocAsync(p, want, cx->alloc_stream) != cudaSuccess) {
         cudaGetLastError();
         want = need;
-        CK(cx, cudaMalloc(p, want));
+        CK(cx, cudaMallocAsync(p, want, cx->alloc_stream));
     }
+    CK(cx, cudaStreamSynchronize(cx->alloc_stream));
     *cap_bytes = want;
     return 0;
 }
@@ -352,7 +422,10 @@ static int launch_zstd_pipeline(zsk_cuda_ctx *cx, zsk_decode_args a, cudaStream_
     const uint64_t dsum = a.dsize_sum ? a.dsize_sum : (uint64_t)njobs << 20;
     int rc;
     if (!cx->scratch) /* deferred frames are rare: one wave of the old kernel is plenty */
-        CK(cx, cudaMalloc((void **)&cx->scratch, (size_t)cx->sm_count * ZSK_LIT_SCRATCH + ZSK_PAD_BACK));
+    {
+        CK(cx, cudaMallocAsync((void **)&cx->scratch, (size_t)cx->sm_count * ZSK_LIT_SCRATCH + ZSK_PAD_BACK, cx->alloc_stream));
+        CK(cx, cudaStreamSynchronize(cx->alloc_stream));
+    }
     if (njobs > cx->zjobs_cap) {
         size_t cap_f = cx->zjobs_cap * sizeof(zsk_zframe), cap_d = cx->zjobs_cap * sizeof(uint32_t);
         if ((rc = grow_pool(cx, (void **)&cx->zframes, &cap_f, njobs * sizeof(zsk_zframe)))) return rc;
@@ -434,7 +507,10 @@ int zsk_cuda_launch_decode(zsk_cuda_ctx *cx, int codec, const zsk_decode_args *a
         zsk_lz4_decode_batch_kernel<<<ctas, ZSK_LZ4_CTA_THREADS, 0, s>>>(a);
         cx->k_name = "zsk_lz4_decode_batch_kernel";
     } else if (codec == ZSK_CODEC_ZSTD && cx->zstd_legacy) {
-        if (!cx->scratch) CK(cx, cudaMalloc((void **)&cx->scratch, (size_t)cx->zstd_ctas * ZSK_LIT_SCRATCH + ZSK_PAD_BACK));
+        if (!cx->scratch) {
+            CK(cx, cudaMallocAsync((void **)&cx->scratch, (size_t)cx->zstd_ctas * ZSK_LIT_SCRATCH + ZSK_PAD_BACK, cx->alloc_stream));
+            CK(cx, cudaStreamSynchronize(cx->alloc_stream));
+        }
         a.scratch = cx->scratch;
         unsigned ctas = a.njobs < (unsigned)cx->zstd_ctas ? a.njobs : (unsigned)cx->zstd_ctas;
         zsk_zstd_decode_kernel<<<ctas, ZSK_ZSTD_CTA_THREADS, 0, s>>>(a);
