@@ -26,6 +26,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <sys/stat.h>
+#include <time.h>
 #include <unistd.h>
 
 #include "../../include/zseek_b200.h"
@@ -503,6 +504,13 @@ static int io_pool_read(io_pool *p, int fd, uint8_t *dst, size_t off, size_t len
     p->len = p->next = 0;
     pthread_mutex_unlock(&p->mu);
     return err;
+}
+
+static double now_ms(void)
+{
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec * 1e3 + ts.tv_nsec / 1e6;
 }
 
 /* ------------------------------------------------------------------ pinned host buffers, allocated on first use */
@@ -1066,11 +1074,14 @@ static ssize_t pread_locked(zseek_reader_t *r, void *buf, size_t count, size_t o
             }
         }
         uint64_t hi = MIN(f + (on_device ? MIN(r->ra_window, r->nslots) : r->ra_window), r->shard_hi);
+        const bool dbg = getenv("ZSEEK_B200_DEBUG") != NULL;
+        const double t_a = dbg ? now_ms() : 0;
         if (!on_device) { /* the window reads are served from is about to be replaced anyway */
             r->mir_lo = r->mir_hi = 0;
             if (!ensure_window(r, r->mir_cur, (size_t)(r->d_off[hi] - r->d_off[f]), errbuf))
                 return -1;
         }
+        const double t_b = dbg ? now_ms() : 0;
         bool ok;
         if (!on_device && hi - f > 1) {
             /* sequential host reader: decode the window through the H2D / decode / D2H pipeline straight into
@@ -1085,6 +1096,9 @@ static ssize_t pread_locked(zseek_reader_t *r, void *buf, size_t count, size_t o
             }
         } else
             ok = fill_window(r, f, hi, !on_device, call_data, errbuf);
+        if (dbg)
+            fprintf(stderr, "[zsk %p] miss: frames [%llu, %llu) window alloc %.2f ms, decode+copy %.2f ms\n", (void *)r, (unsigned long long)f,
+                    (unsigned long long)hi, t_b - t_a, now_ms() - t_b);
         if (!ok) {
             /* the reference decodes only the frame a call asks for (src/decompress.c:700-790): a bad frame further
              * ahead in the window must not fail this read.  Forget the window and decode frame f alone. */

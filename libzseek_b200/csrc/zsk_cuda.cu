@@ -24,6 +24,7 @@ struct zsk_cuda_ctx {
     cudaStream_t alloc_stream;            /* cudaMallocAsync / cudaFreeAsync */
     cudaStream_t streams[ZSK_NSTREAMS + 1];   /* + ZSK_STREAM_USER: caller-owned, never created or destroyed here */
     cudaEvent_t sync_ev;                 /* cross-stream dependencies */
+    cudaEvent_t block_ev[ZSK_NSTREAMS + 1]; /* host waits: blocking events, so that a waiting caller thread sleeps instead of spinning */
     cudaEvent_t user_ev[ZSK_NEVENTS];
     cudaEvent_t t0, t1;                  /* zsk_cuda_timer_* */
     cudaEvent_t k0, k1;                  /* around the most recent decode kernel */
@@ -120,11 +121,14 @@ int zsk_cuda_ctx_create(int device, zsk_cuda_ctx **out, char *err, size_t errlen
         CK0(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
     }
     CK0(cudaEventCreateWithFlags(&cx->sync_ev, cudaEventDisableTiming));
-    for (int i = 0; i < ZSK_NEVENTS; i++) CK0(cudaEventCreateWithFlags(&cx->user_ev[i], cudaEventDisableTiming));
-    CK0(cudaEventCreate(&cx->t0));
-    CK0(cudaEventCreate(&cx->t1));
-    CK0(cudaEventCreate(&cx->k0));
-    CK0(cudaEventCreate(&cx->k1));
+    /* every host wait goes through a BLOCKING event: with one reader per caller thread and the threads pinned to all cores,
+     * spinning waits starved the driver's own threads (measured: 100-2,000 ms for a one-frame miss at 16 threads) */
+    for (int i = 0; i <= ZSK_NSTREAMS; i++) CK0(cudaEventCreateWithFlags(&cx->block_ev[i], cudaEventDisableTiming | cudaEventBlockingSync));
+    for (int i = 0; i < ZSK_NEVENTS; i++) CK0(cudaEventCreateWithFlags(&cx->user_ev[i], cudaEventDisableTiming | cudaEventBlockingSync));
+    CK0(cudaEventCreateWithFlags(&cx->t0, cudaEventBlockingSync));
+    CK0(cudaEventCreateWithFlags(&cx->t1, cudaEventBlockingSync));
+    CK0(cudaEventCreateWithFlags(&cx->k0, cudaEventBlockingSync));
+    CK0(cudaEventCreateWithFlags(&cx->k1, cudaEventBlockingSync));
     CK0(cudaMallocAsync((void **)&cx->counters, ZSK_NCOUNTERS * sizeof(uint32_t), cx->alloc_stream));
     int per_sm = 0;
     CK0(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, zsk_zstd_decode_kernel, ZSK_ZSTD_CTA_THREADS, 0));
@@ -194,6 +198,7 @@ void zsk_cuda_ctx_destroy(zsk_cuda_ctx *cx)
         cudaStreamDestroy(cx->streams[i]);
     }
     cudaEventDestroy(cx->sync_ev);
+    for (int i = 0; i <= ZSK_NSTREAMS; i++) cudaEventDestroy(cx->block_ev[i]);
     for (int i = 0; i < ZSK_NEVENTS; i++) cudaEventDestroy(cx->user_ev[i]);
     cudaEventDestroy(cx->t0);
     cudaEventDestroy(cx->t1);
@@ -342,7 +347,9 @@ int zsk_cuda_memcpy_async(zsk_cuda_ctx *cx, void *dst, const void *src, size_t n
 
 int zsk_cuda_stream_sync(zsk_cuda_ctx *cx, int stream)
 {
-    CK(cx, cudaStreamSynchronize(cx->streams[stream]));
+    CK(cx, cudaSetDevice(cx->device));
+    CK(cx, cudaEventRecord(cx->block_ev[stream], cx->streams[stream]));
+    CK(cx, cudaEventSynchronize(cx->block_ev[stream]));
     return 0;
 }
 

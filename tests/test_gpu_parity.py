@@ -385,6 +385,91 @@ def test_file_opened_by_path_uses_parallel_ingest_and_decodes_identically(lib, c
             del os.environ["ZSEEK_B200_IO_THREADS"]
 
 
+def test_hbm_cache_honours_capacity_and_evicts_least_recently_used(lib, torch_cuda):
+    """Restates reference test/test_cache.c:135-159 (capacity 3, four inserts: the first one is gone, the other three are
+    found) for the HBM frame cache, through the API: capacity C = cache_size, C + 1 distinct frames read in an order no
+    read-ahead follows, then hits and the one miss are told apart by whether a read launches a kernel.  Also what the
+    reference's list gets wrong: a hit promotes, so the promoted frame survives the next eviction, and
+    cached_frames never exceeds the capacity."""
+    torch = torch_cuda
+    from datagen import refwriter, zsyn
+    if not have_reference():
+        pytest.skip("inputs come from the reference writer (oracle/_ref)")
+    data = zsyn.gen(160 * 8192, seed=5)
+    image = refwriter.write(data, LZ4, 0, 8192)
+    C_ = 70
+    buf = torch.zeros(8192, dtype=torch.uint8, device="cuda")
+    with lib.Reader(image=image, cache_size=C_) as rd:
+        assert rd.frames == 160
+        rd.load(0, rd.frames)
+
+        def read(f):
+            l0 = rd.launch_count
+            assert rd.pread_into(buf, 100, f * 8192 + 7) == 100
+            assert buf[:100].cpu().numpy().tobytes() == data[f * 8192 + 7:f * 8192 + 107]
+            return rd.launch_count > l0       # True = a kernel ran = miss
+
+        order = list(range(2 * C_, -1, -2))[:C_ + 1]          # C + 1 distinct frames, descending by 2: never sequential
+        assert all(read(f) for f in order[:C_])               # all misses
+        assert rd.stats().cached_frames == C_
+        assert not read(order[0])                             # hit: promotes the oldest entry to most recently used
+        assert read(order[C_])                                # one more frame: evicts the least recently used = order[1]
+        assert rd.stats().cached_frames == C_
+        assert not read(order[0]) and not read(order[C_])     # the promoted and the new frame are there
+        for f in order[2:C_]:
+            assert not read(f), f                             # so is everything younger than the victim
+        assert read(order[1])                                 # the victim is gone
+        assert rd.stats().cached_frames == C_
+
+
+@pytest.mark.parametrize("name", ["zsyn_lz4_64k", "zsyn_lz4_256k_linked", "mix_lz4", "zsyn_zstd3_128k", "zsyn_zstd19_256k", "zsyn_zstd3_mt",
+                                  "mix_zstd3", "mix_zstd19"])
+def test_bit_flip_fuzz_never_crashes_and_never_lies(lib, golden, name, monkeypatch, torch_cuda):
+    """Random single-bit flips over every golden file, every shipped decode kernel: the call returns (no hang, no sticky
+    CUDA error: the next read works), frames the flip did not touch decode to the reference bytes, and the frame that holds
+    the flip is either rejected or decodes to bytes of the claimed size (whatever they are) — never an out-of-bounds write
+    (guard bytes)."""
+    torch = torch_cuda
+    cases, _ = golden
+    c = cases[name]
+    with OraclePort(c["image"]) as op:
+        good = op.decode_all()
+        c_off, d_off, nfr, codec = op.c_off.astype(np.int64), op.d_off.astype(np.int64), op.frames, op.codec
+    payload = int(c_off[-1])
+    rng = np.random.Generator(np.random.PCG64(99))
+    envs = [{"ZSEEK_B200_LZ4_LANE_MIN": "0"}, {"ZSEEK_B200_LZ4_LANE_MIN": "4000000000"}] if codec == LZ4 else [{}, {"ZSEEK_B200_ZSTD_LEGACY": "1"}]
+    for env in envs:
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        for trial in range(25):
+            img = bytearray(c["image"])
+            pos = int(rng.integers(0, payload))
+            img[pos] ^= 1 << int(rng.integers(0, 8))
+            hit = int(np.searchsorted(c_off, pos, side="right")) - 1
+            with lib.Reader(image=bytes(img), cache_size=0) as rd:
+                dev = torch.full((int(d_off[-1]) + 256,), 0xEE, dtype=torch.uint8, device="cuda")
+                try:
+                    rd.decode_frames(0, nfr, dev[128:])
+                    rejected = False
+                except lib.ZseekError as e:
+                    assert str(e).startswith("decompress frame"), str(e)
+                    rejected = True
+                got = dev.cpu().numpy()
+                assert (got[:128] == 0xEE).all() and (got[128 + int(d_off[-1]):] == 0xEE).all(), (name, env, pos)
+                for f in range(nfr):
+                    if f != hit:
+                        a, b = int(d_off[f]), int(d_off[f + 1])
+                        assert (got[128 + a:128 + b] == good[a:b]).all(), (name, env, pos, f)
+                if not rejected:   # the flipped frame decoded to the claimed size; usually a checksum-less format cannot tell
+                    pass
+                # the reader (and the CUDA context) is still usable
+                f2 = (hit + 1) % nfr
+                r, bts = rd.pread(50, int(d_off[f2]))
+                assert bts == good[int(d_off[f2]):int(d_off[f2]) + r].tobytes()
+        for k in env:
+            monkeypatch.delenv(k)
+
+
 # --------------------------------------------------------------------------- every LZ4 kernel, whatever the launch size
 LZ4_KERNEL_ENVS = {
     "lane_per_frame": {"ZSEEK_B200_LZ4_LANE_MIN": "0", "ZSEEK_B200_SORT_MIN": "0"},           # the kernel big launches get
