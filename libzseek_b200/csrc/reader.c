@@ -20,6 +20,7 @@
 #include <errno.h>
 #include <pthread.h>
 #include <stdarg.h>
+#include <stdatomic.h>
 #include <stdbool.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -62,6 +63,8 @@ struct zseek_reader {
     /* device */
     zsk_cuda_ctx *cx;
     uint64_t *g_coff, *g_doff;
+    size_t n_cap;      /* entries g_coff / g_doff / g_frame_src hold */
+    size_t slab_bytes; /* bytes of g_slab */
 
     /* shard */
     uint64_t shard_lo, shard_hi;
@@ -72,8 +75,8 @@ struct zseek_reader {
     uint64_t res_lo, res_hi;
 
     /* pinned host staging */
-    uint8_t *h_stage; /* two halves */
-    size_t stage_half;
+    uint8_t *h_stage; /* two halves of stage_half bytes (grown on demand up to stage_half_max) */
+    size_t stage_half, stage_half_max;
     int stage_next, stage_inflight;
     uint8_t *h_mir[2]; /* two pinned windows of mir_cap[] bytes; window mir_cur holds the decoded bytes of frames [mir_lo, mir_hi) */
     size_t mir_cap[2];
@@ -131,7 +134,9 @@ struct zseek_reader {
     uint32_t random_misses, resident_after;
     size_t resident_max;
     bool resident_tried, resident;
+    size_t resident_bytes; /* what this reader added to g_resident_bytes */
     size_t window_cap; /* most bytes an ordinary read-ahead window holds */
+    bool counted;      /* this reader is in g_live_readers */
 
     /* read-ahead */
     uint64_t ra_next;
@@ -150,6 +155,21 @@ struct zseek_reader {
     uintptr_t ptr_block[8];
     int8_t ptr_is_dev[8];
 };
+
+/* Process-wide bookkeeping for callers that keep one reader per thread: pinned host memory is the scarce resource (it is
+ * slow to create and every reader wants two decoded windows of it), so the size of a read-ahead window follows the number
+ * of live readers, and whole-shard residency draws from one process-wide budget. */
+static atomic_uint g_live_readers;
+static atomic_size_t g_resident_bytes;
+
+/* Closed readers are PARKED, not destroyed: the next zseek_reader_open* of the process takes over the device context (streams,
+ * events, the zstd scratch pools), the device buffers and the pinned windows of a parked one.  A caller that opens one
+ * reader per thread (or per request) otherwise pays ~20 allocations, each under the driver's process-wide lock, on the
+ * first read of every reader: measured 12-19 ms for a one-frame miss with 16 threads, against 1.3 ms alone. */
+#define ZSK_MAX_PARKED 64
+static pthread_mutex_t g_park_mu = PTHREAD_MUTEX_INITIALIZER;
+static struct zseek_reader *g_parked[ZSK_MAX_PARKED];
+static int g_nparked;
 
 /* ------------------------------------------------------------------ errors (reference src/common.c:45-54) */
 static bool stream_frames_finish(zseek_reader_t *r, uint64_t lo, uint64_t hi, bool resident, bool ok, char *errbuf);
@@ -514,13 +534,39 @@ static double now_ms(void)
 }
 
 /* ------------------------------------------------------------------ pinned host buffers, allocated on first use */
-static bool ensure_stage(zseek_reader_t *r, char *errbuf)
+/* two pinned staging halves, each large enough for min(bytes, stage_half_max): a reader that only ever pulls small windows
+ * through its callback never pins the full 2 x 32 MiB */
+static bool ensure_stage(zseek_reader_t *r, size_t bytes, char *errbuf)
 {
-    if (r->h_stage)
+    size_t want = MIN(r->stage_half_max, MAX(MAX(bytes, (size_t)r->max_csize), (size_t)1 << 20));
+    if (r->h_stage && want <= r->stage_half)
         return true;
-    if (zsk_cuda_malloc_host(r->cx, (void **)&r->h_stage, 2 * r->stage_half))
+    want = MIN(r->stage_half_max, MAX(want, 2 * r->stage_half));
+    if (r->h_stage) {
+        if (zsk_cuda_stream_sync(r->cx, ZSK_STREAM_H2D)) return cuda_fail(r, errbuf, "synchronize");
+        r->stage_inflight = 0;
+        zsk_cuda_free_host(r->cx, r->h_stage);
+        r->h_stage = NULL;
+    }
+    r->stage_half = 0;
+    if (zsk_cuda_malloc_host(r->cx, (void **)&r->h_stage, 2 * want))
         return cuda_fail(r, errbuf, "allocate pinned staging");
+    r->stage_half = want;
+    r->stage_next = 0;
     return true;
+}
+
+/* most frames an ordinary read-ahead window may hold right now: the reader's own maximum, cut down so that the two pinned
+ * windows of every live reader of the process fit ZSEEK_B200_WINDOW_BUDGET_MB (default 2048) together */
+static uint32_t ra_limit(const zseek_reader_t *r)
+{
+    static size_t budget;
+    if (!budget)
+        budget = MAX(env_size("ZSEEK_B200_WINDOW_BUDGET_MB", 2048), 1) << 20;
+    const unsigned live = MAX(atomic_load(&g_live_readers), 1u);
+    const size_t per_window = MAX(budget / (2 * (size_t)live), (size_t)8 << 20);
+    const size_t frames = per_window / MAX((size_t)r->max_dsize, 1);
+    return (uint32_t)MAX(1, MIN((size_t)r->ra_max, frames));
 }
 
 /* pinned window `which` of at least `bytes` (grown geometrically up to window_cap: a reader that only ever sees small
@@ -530,7 +576,11 @@ static bool ensure_window(zseek_reader_t *r, int which, size_t bytes, char *errb
     if (r->h_mir[which] && bytes <= r->mir_cap[which])
         return true;
     zsk_cuda_stream_sync(r->cx, ZSK_STREAM_D2H);
-    size_t cap = MAX(bytes, MIN(r->window_cap, MAX(2 * r->mir_cap[which], (size_t)4 << 20)));
+    /* two sizes only — 4 MiB for the first windows of a scan (and for random readers), then the largest window this reader
+     * may use right now — so that a scan pins each of its windows at most twice */
+    size_t cap = MAX(bytes, (size_t)4 << 20);
+    if (bytes > ((size_t)4 << 20))
+        cap = MAX(bytes, MIN(r->window_cap, (size_t)ra_limit(r) * r->max_dsize));
     zsk_cuda_free_host(r->cx, r->h_mir[which]);
     r->h_mir[which] = NULL;
     r->mir_cap[which] = 0;
@@ -554,7 +604,7 @@ static bool h2d_range(zseek_reader_t *r, size_t file_off, size_t bytes, uint8_t 
             return cuda_fail(r, errbuf, "copy image to device");
         return true;
     }
-    if (!ensure_stage(r, errbuf))
+    if (!ensure_stage(r, bytes, errbuf))
         return false;
     size_t done = 0;
     while (done < bytes) {
@@ -775,19 +825,124 @@ static bool in_shard(zseek_reader_t *r, uint64_t f, char *errbuf)
 }
 
 /* ------------------------------------------------------------------ open / close */
-static void reader_free(zseek_reader_t *r)
+/* waits for everything the reader queued and takes it out of the process-wide counts */
+static void reader_quiesce(zseek_reader_t *r)
 {
-    if (!r)
-        return;
     if (r->cx)
         prefetch_drop(r);
+    if (r->counted)
+        atomic_fetch_sub(&g_live_readers, 1u);
+    r->counted = false;
+    if (r->resident_bytes)
+        atomic_fetch_sub(&g_resident_bytes, r->resident_bytes);
+    r->resident_bytes = 0;
     io_pool_destroy(r->io);
+    r->io = NULL;
     if (r->cx && r->async_stream >= 0)
         zsk_cuda_stream_sync(r->cx, r->async_stream);
+    r->async_stream = -1;
     if (r->cx) {
         zsk_cuda_stream_sync(r->cx, ZSK_STREAM_COMPUTE);
         zsk_cuda_stream_sync(r->cx, ZSK_STREAM_H2D);
         zsk_cuda_stream_sync(r->cx, ZSK_STREAM_D2H);
+    }
+}
+
+static void free_file_state(zseek_reader_t *r)
+{
+    free(r->c_off); free(r->d_off);
+    free(r->slot_frame); free(r->lru_prev); free(r->lru_next); free(r->frame_slot); free(r->valid_len);
+    free(r->h_frame_src); free(r->h_touched);
+    r->c_off = r->d_off = NULL;
+    r->slot_frame = r->lru_prev = r->lru_next = r->frame_slot = NULL;
+    r->valid_len = NULL;
+    r->h_frame_src = NULL;
+    r->h_touched = NULL;
+}
+
+/* Keeps the device side of a closed reader for the next open: context, seek-table / slab / image / staging / job buffers
+ * and the pinned windows with their capacities; everything that describes the file is dropped.  Large buffers are given
+ * back so that a parked reader holds at most a few hundred MiB.  false: not parkable (the caller destroys it). */
+static bool reader_park(zseek_reader_t *r)
+{
+    static int enabled = -1;
+    if (enabled < 0)
+        enabled = env_size("ZSEEK_B200_PARK", 1) != 0;
+    if (!enabled || !r->cx)
+        return false;
+    reader_quiesce(r);
+    free_file_state(r);
+    const size_t keep_max = (size_t)256 << 20;
+    /* buffers whose size depends on the file's frame geometry in ways the next file need not share, and the big ones */
+    void *drop[] = { r->g_touched, r->g_bslab, r->g_bjob_ids, r->g_bjob_limits, r->g_bctl, r->g_bjob_offs, r->g_bjob_status, r->g_bsrc,
+                     r->g_comp_cap > keep_max ? r->g_comp : NULL, r->g_out_cap > keep_max ? r->g_out : NULL,
+                     r->slab_bytes > keep_max ? r->g_slab : NULL };
+    for (size_t i = 0; i < sizeof(drop) / sizeof(drop[0]); i++)
+        zsk_cuda_free(r->cx, drop[i]);
+    zseek_reader_t k;
+    memset(&k, 0, sizeof(k));
+    k.cx = r->cx;
+    k.g_coff = r->g_coff; k.g_doff = r->g_doff; k.g_frame_src = r->g_frame_src; k.n_cap = r->n_cap;
+    if (r->slab_bytes <= keep_max) { k.g_slab = r->g_slab; k.slab_bytes = r->slab_bytes; }
+    if (r->g_comp_cap <= keep_max) { k.g_comp = r->g_comp; k.g_comp_cap = r->g_comp_cap; }
+    if (r->g_out_cap <= keep_max) { k.g_out = r->g_out; k.g_out_cap = r->g_out_cap; }
+    k.h_stage = r->h_stage; k.stage_half = r->stage_half;
+    for (int w = 0; w < 2; w++) {
+        if (r->mir_cap[w] <= keep_max) { k.h_mir[w] = r->h_mir[w]; k.mir_cap[w] = r->mir_cap[w]; }
+        else zsk_cuda_free_host(r->cx, r->h_mir[w]); /* a whole-shard window: back to the pinned cache */
+    }
+    k.job_cap = r->job_cap;
+    k.g_job_ids = r->g_job_ids; k.g_job_offs = r->g_job_offs; k.g_job_limits = r->g_job_limits; k.g_job_status = r->g_job_status;
+    k.h_job_ids = r->h_job_ids; k.h_job_offs = r->h_job_offs; k.h_job_limits = r->h_job_limits; k.h_job_status = r->h_job_status;
+    k.batch_cap = r->batch_cap;
+    k.g_b_offsets = r->g_b_offsets; k.g_b_counts = r->g_b_counts; k.g_b_dstoffs = r->g_b_dstoffs;
+    k.g_b_frame = r->g_b_frame; k.g_b_inframe = r->g_b_inframe; k.g_b_nbytes = r->g_b_nbytes;
+    zsk_cuda_ctx_trim(k.cx, keep_max);
+    pthread_mutex_destroy(&r->lock);
+    *r = k;
+    pthread_mutex_lock(&g_park_mu);
+    const bool parked = g_nparked < ZSK_MAX_PARKED;
+    if (parked)
+        g_parked[g_nparked++] = r;
+    pthread_mutex_unlock(&g_park_mu);
+    if (!parked)
+        pthread_mutex_init(&r->lock, NULL); /* reader_free destroys it */
+    return parked;
+}
+
+static void reader_free(zseek_reader_t *r);
+
+/* a zeroed reader, or a parked one of the device the next context would use */
+static zseek_reader_t *reader_new(void)
+{
+    zseek_reader_t *r = NULL;
+    pthread_mutex_lock(&g_park_mu);
+    const int dev = g_nparked ? zsk_cuda_pick_device() : -1; /* no device call before the file has been looked at otherwise */
+    for (int i = g_nparked - 1; i >= 0 && dev >= 0; i--)
+        if (zsk_cuda_device(g_parked[i]->cx) == dev) {
+            r = g_parked[i];
+            g_parked[i] = g_parked[--g_nparked];
+            break;
+        }
+    pthread_mutex_unlock(&g_park_mu);
+    if (r && zsk_cuda_ctx_reuse(r->cx)) { /* the parked context is unusable: start afresh */
+        pthread_mutex_init(&r->lock, NULL);
+        reader_free(r);
+        r = NULL;
+    }
+    if (!r)
+        r = calloc(1, sizeof(*r));
+    if (r)
+        pthread_mutex_init(&r->lock, NULL);
+    return r;
+}
+
+static void reader_free(zseek_reader_t *r)
+{
+    if (!r)
+        return;
+    reader_quiesce(r);
+    if (r->cx) {
         void *dev[] = { r->g_coff, r->g_doff, r->g_comp, r->g_slab, r->g_frame_src, r->g_job_ids, r->g_job_offs, r->g_job_status, r->g_job_limits,
                         r->g_b_offsets, r->g_b_counts, r->g_b_dstoffs, r->g_b_frame, r->g_b_inframe, r->g_b_nbytes, r->g_touched,
                         r->g_out, r->g_bslab, r->g_bjob_ids, r->g_bjob_limits, r->g_bctl, r->g_bjob_offs, r->g_bjob_status, r->g_bsrc };
@@ -798,9 +953,7 @@ static void reader_free(zseek_reader_t *r)
             zsk_cuda_free_host(r->cx, pin[i]);
         zsk_cuda_ctx_destroy(r->cx);
     }
-    free(r->c_off); free(r->d_off);
-    free(r->slot_frame); free(r->lru_prev); free(r->lru_next); free(r->frame_slot); free(r->valid_len);
-    free(r->h_frame_src); free(r->h_touched);
+    free_file_state(r);
     pthread_mutex_destroy(&r->lock);
     free(r);
 }
@@ -840,7 +993,7 @@ static zseek_reader_t *reader_open_common(zseek_reader_t *r, size_t cache_size, 
         goto fail;
     }
     char derr[128];
-    if (zsk_cuda_ctx_create(-1, &r->cx, derr, sizeof(derr))) { /* no CPU fallback: fail loudly */
+    if (!r->cx && zsk_cuda_ctx_create(-1, &r->cx, derr, sizeof(derr))) { /* no CPU fallback: fail loudly (a parked reader brings its context) */
         set_error(errbuf, "context creation failed: %s", derr);
         goto fail;
     }
@@ -867,9 +1020,9 @@ static zseek_reader_t *reader_open_common(zseek_reader_t *r, size_t cache_size, 
     r->slot_size = ((size_t)r->max_dsize + 255) & ~(size_t)255;
     if (r->slot_size == 0)
         r->slot_size = 256;
-    r->stage_half = env_size("ZSEEK_B200_STAGE_MB", 64) * (1u << 20) / 2;
-    if (r->stage_half < r->max_csize)
-        r->stage_half = r->max_csize;
+    r->stage_half_max = env_size("ZSEEK_B200_STAGE_MB", 64) * (1u << 20) / 2;
+    if (r->stage_half_max < r->max_csize)
+        r->stage_half_max = r->max_csize;
     r->window_cap = (size_t)r->ra_max * r->max_dsize;
     r->chunk_bytes = env_size("ZSEEK_B200_CHUNK_MB", 512) << 20;
     r->ramp_bytes = env_size("ZSEEK_B200_RAMP_MB", 16) << 20;
@@ -899,14 +1052,33 @@ static zseek_reader_t *reader_open_common(zseek_reader_t *r, size_t cache_size, 
     }
     r->frame_src_dirty = true;
 
-    if (zsk_cuda_malloc(r->cx, (void **)&r->g_coff, (N + 1) * sizeof(uint64_t)) ||
-        zsk_cuda_malloc(r->cx, (void **)&r->g_doff, (N + 1) * sizeof(uint64_t)) ||
-        zsk_cuda_malloc(r->cx, (void **)&r->g_frame_src, (N + 1) * sizeof(int64_t)) ||
-        zsk_cuda_malloc(r->cx, (void **)&r->g_slab, (size_t)r->nslots * r->slot_size + ZSK_PAD_FRONT + ZSK_PAD_BACK)) {
-        /* the pinned ingest staging (h_stage) and the pinned decoded windows (h_mir[]) are allocated on first use:
-         * readers that only serve device buffers or batches never pay for them */
-        set_error(errbuf, "buffer creation failed: %s", zsk_cuda_error(r->cx));
-        goto fail;
+    /* the pinned ingest staging (h_stage) and the pinned decoded windows (h_mir[]) are allocated on first use: readers
+     * that only serve device buffers or batches never pay for them.  A parked reader's buffers are kept when they are
+     * large enough. */
+    if (r->n_cap < N + 1) {
+        zsk_cuda_free(r->cx, r->g_coff); zsk_cuda_free(r->cx, r->g_doff); zsk_cuda_free(r->cx, r->g_frame_src);
+        r->g_coff = r->g_doff = NULL;
+        r->g_frame_src = NULL;
+        r->n_cap = 0;
+        const size_t cap = MAX(N + 1, 4096);
+        if (zsk_cuda_malloc(r->cx, (void **)&r->g_coff, cap * sizeof(uint64_t)) ||
+            zsk_cuda_malloc(r->cx, (void **)&r->g_doff, cap * sizeof(uint64_t)) ||
+            zsk_cuda_malloc(r->cx, (void **)&r->g_frame_src, cap * sizeof(int64_t))) {
+            set_error(errbuf, "buffer creation failed: %s", zsk_cuda_error(r->cx));
+            goto fail;
+        }
+        r->n_cap = cap;
+    }
+    const size_t slab_need = (size_t)r->nslots * r->slot_size + ZSK_PAD_FRONT + ZSK_PAD_BACK;
+    if (r->slab_bytes < slab_need) {
+        zsk_cuda_free(r->cx, r->g_slab);
+        r->g_slab = NULL;
+        r->slab_bytes = 0;
+        if (zsk_cuda_malloc(r->cx, (void **)&r->g_slab, slab_need)) {
+            set_error(errbuf, "buffer creation failed: %s", zsk_cuda_error(r->cx));
+            goto fail;
+        }
+        r->slab_bytes = slab_need;
     }
     if (zsk_cuda_memcpy_async(r->cx, r->g_coff, r->c_off, (N + 1) * sizeof(uint64_t), ZSK_H2D, ZSK_STREAM_COMPUTE) ||
         zsk_cuda_memcpy_async(r->cx, r->g_doff, r->d_off, (N + 1) * sizeof(uint64_t), ZSK_H2D, ZSK_STREAM_COMPUTE) ||
@@ -914,6 +1086,8 @@ static zseek_reader_t *reader_open_common(zseek_reader_t *r, size_t cache_size, 
         set_error(errbuf, "seek table upload failed: %s", zsk_cuda_error(r->cx));
         goto fail;
     }
+    atomic_fetch_add(&g_live_readers, 1u);
+    r->counted = true;
     return r;
 fail:
     reader_free(r);
@@ -923,12 +1097,11 @@ fail:
 zseek_reader_t *zseek_reader_open_full(zseek_read_file_t user_file, size_t cache_size, void *call_data,
                                        char errbuf[ZSEEK_ERRBUF_SIZE])
 {
-    zseek_reader_t *r = calloc(1, sizeof(*r));
+    zseek_reader_t *r = reader_new();
     if (!r) {
         set_error(errbuf, "allocate reader: %s", strerror(errno));
         return NULL;
     }
-    pthread_mutex_init(&r->lock, NULL);
     r->user_file = user_file;
     r->file_fd = -1;
     return reader_open_common(r, cache_size, call_data, errbuf);
@@ -936,12 +1109,11 @@ zseek_reader_t *zseek_reader_open_full(zseek_read_file_t user_file, size_t cache
 
 zseek_reader_t *zseek_reader_open(FILE *cfile, size_t cache_size, void *call_data, char errbuf[ZSEEK_ERRBUF_SIZE])
 {
-    zseek_reader_t *r = calloc(1, sizeof(*r));
+    zseek_reader_t *r = reader_new();
     if (!r) {
         set_error(errbuf, "allocate reader: %s", strerror(errno));
         return NULL;
     }
-    pthread_mutex_init(&r->lock, NULL);
     r->user_file = (zseek_read_file_t){ cfile, file_pread, file_fsize };
     r->file_fd = cfile ? fileno(cfile) : -1; /* large ingests read the descriptor with pread(2) from worker threads */
     return reader_open_common(r, cache_size, call_data, errbuf);
@@ -949,12 +1121,11 @@ zseek_reader_t *zseek_reader_open(FILE *cfile, size_t cache_size, void *call_dat
 
 zseek_reader_t *zseek_b200_reader_open_mem(const void *image, size_t size, size_t cache_size, char errbuf[ZSEEK_ERRBUF_SIZE])
 {
-    zseek_reader_t *r = calloc(1, sizeof(*r));
+    zseek_reader_t *r = reader_new();
     if (!r) {
         set_error(errbuf, "allocate reader: %s", strerror(errno));
         return NULL;
     }
-    pthread_mutex_init(&r->lock, NULL);
     r->mem_image = image;
     r->mem_size = size;
     r->file_fd = -1;
@@ -968,7 +1139,8 @@ bool zseek_reader_close(zseek_reader_t *reader, void *call_data, char errbuf[ZSE
     (void)errbuf;
     if (!reader)
         return true;
-    reader_free(reader);
+    if (!reader_park(reader))
+        reader_free(reader);
     return true;
 }
 
@@ -982,14 +1154,22 @@ static bool go_resident(zseek_reader_t *r, void *call_data)
     const size_t bytes = (size_t)(r->d_off[r->shard_hi] - r->d_off[r->shard_lo]);
     if (bytes == 0)
         return false;
+    /* the budget (ZSEEK_B200_RESIDENT_MB) is shared by the readers of the process: sixteen readers of one file must not
+     * pin sixteen decoded copies of it */
+    if (atomic_fetch_add(&g_resident_bytes, bytes) + bytes > r->resident_max) {
+        atomic_fetch_sub(&g_resident_bytes, bytes);
+        return false;
+    }
+    r->resident_bytes = bytes;
     prefetch_drop(r);
     zsk_cuda_stream_sync(r->cx, ZSK_STREAM_COMPUTE);
     zsk_cuda_stream_sync(r->cx, ZSK_STREAM_D2H);
     uint8_t *win = NULL;
-    if (zsk_cuda_malloc_host(r->cx, (void **)&win, bytes))
-        return false;
-    if (!stream_frames_to_host(r, r->shard_lo, r->shard_hi, win, call_data, scratch)) {
+    if (zsk_cuda_malloc_host(r->cx, (void **)&win, bytes) ||
+        !stream_frames_to_host(r, r->shard_lo, r->shard_hi, win, call_data, scratch)) {
         zsk_cuda_free_host(r->cx, win);
+        atomic_fetch_sub(&g_resident_bytes, r->resident_bytes);
+        r->resident_bytes = 0;
         return false;
     }
     zsk_cuda_free_host(r->cx, r->h_mir[0]);
@@ -1017,6 +1197,8 @@ static void drop_resident(zseek_reader_t *r)
     r->mir_cur = 0;
     r->resident = r->resident_tried = false;
     r->random_misses = 0;
+    atomic_fetch_sub(&g_resident_bytes, r->resident_bytes);
+    r->resident_bytes = 0;
 }
 
 /* ------------------------------------------------------------------ zseek_pread (reference src/decompress.c:806-824) */
@@ -1041,12 +1223,18 @@ static ssize_t pread_locked(zseek_reader_t *r, void *buf, size_t count, size_t o
         /* the scan reached the window that was being decoded behind its back: wait for it, swap halves, and queue
          * the window after it before copying this call's bytes */
         r->pf_active = false;
+        const bool dbg = getenv("ZSEEK_B200_DEBUG") != NULL;
+        const double t_a = dbg ? now_ms() : 0;
         if (stream_frames_finish(r, r->pf_lo, r->pf_hi, r->pf_resident, r->pf_ok, errbuf)) {
+            const double t_b = dbg ? now_ms() : 0;
             r->mir_cur ^= 1;
             r->mir_lo = r->pf_lo;
             r->mir_hi = r->pf_hi;
             r->ra_next = r->pf_hi;
             prefetch_start(r, call_data);
+            if (dbg)
+                fprintf(stderr, "[zsk %p] read-ahead window [%llu, %llu): waited %.2f ms, queued the next one in %.2f ms\n", (void *)r,
+                        (unsigned long long)r->mir_lo, (unsigned long long)r->mir_hi, t_b - t_a, now_ms() - t_b);
             memcpy(buf, mirror_half(r, r->mir_cur) + (offset - r->d_off[r->mir_lo]), n);
             return (ssize_t)n;
         }
@@ -1060,7 +1248,7 @@ static ssize_t pread_locked(zseek_reader_t *r, void *buf, size_t count, size_t o
         /* miss: decode a window of frames in one launch; the window grows while the access pattern
          * stays sequential and collapses to a single frame on a random access */
         if (f == r->ra_next)
-            r->ra_window = MIN(r->ra_window * 8, r->ra_max); /* a launch costs ~10 ms whatever its size: grow fast */
+            r->ra_window = MIN(r->ra_window * 8, ra_limit(r)); /* a launch costs about the same whatever its size: grow fast */
         else
             r->ra_window = 1;
         if (!on_device && r->ra_window == 1 && !r->resident_tried && r->resident_after && ++r->random_misses >= r->resident_after &&
@@ -1510,7 +1698,7 @@ static void prefetch_start(zseek_reader_t *r, void *call_data)
 {
     if (r->pf_active || r->mir_hi <= r->mir_lo || r->mir_hi >= r->shard_hi || r->mir_hi - r->mir_lo < 4)
         return;
-    r->ra_window = MIN(r->ra_window * 8, r->ra_max);
+    r->ra_window = MIN(r->ra_window * 8, ra_limit(r));
     uint64_t lo = r->mir_hi, hi = MIN(lo + r->ra_window, r->shard_hi);
     char scratch[ZSEEK_ERRBUF_SIZE]; /* a failing read-ahead is not an error of this call: the window is retried synchronously */
     if (!ensure_window(r, r->mir_cur ^ 1, (size_t)(r->d_off[hi] - r->d_off[lo]), scratch))

@@ -18,6 +18,21 @@
 
 #define ZSK_NCOUNTERS 64
 
+#include <time.h>
+/* ZSEEK_B200_DEBUG=1: slow allocations are reported on stderr */
+static int zsk_dbg(void)
+{
+    static int v = -1;
+    if (v < 0) v = getenv("ZSEEK_B200_DEBUG") != NULL;
+    return v;
+}
+static double zsk_now_ms(void)
+{
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec * 1e3 + ts.tv_nsec / 1e6;
+}
+
 struct zsk_cuda_ctx {
     int device;
     int sm_count;
@@ -52,7 +67,7 @@ struct zsk_cuda_ctx {
     int lz4_lane_ctas;                   /* resident CTAs of the lane-per-frame kernel */
     unsigned lz4_lane_min;               /* launches with at least this many frames use the lane-per-frame kernel */
     unsigned long long launches;
-    int trace;                           /* ZSEEK_B200_TRACE=1: timeline of the host-destination pipeline */
+    int trace, trace_ready;              /* ZSEEK_B200_TRACE=1: timeline of the host-destination pipeline */
     cudaEvent_t trace_ev[ZSK_NTRACE];
     const char *trace_what[ZSK_NTRACE];
     unsigned trace_k[ZSK_NTRACE], trace_n;
@@ -70,20 +85,151 @@ struct zsk_cuda_ctx {
 
 extern "C" {
 
+/* the device a context created now would use: ZSEEK_B200_DEVICE, else LOCAL_RANK, else the current CUDA device; -1 without one */
+int zsk_cuda_pick_device(void)
+{
+    int ndev = 0, device = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return -1;
+    }
+    const char *s = getenv("ZSEEK_B200_DEVICE");
+    if (!s) s = getenv("LOCAL_RANK");
+    if (s) device = atoi(s) % ndev;
+    else if (cudaGetDevice(&device) != cudaSuccess) device = 0;
+    return device;
+}
+
+/* launch geometry and tuning knobs (environment); run when a context is created and again when a parked one is reused.
+ * The occupancy figures are properties of the kernels and the device: asked once per device. */
+static int ctx_configure(zsk_cuda_ctx *cx, char *err, size_t errlen)
+{
+    enum { K_ZSTD = 0, K_FSE, K_HUF, K_EXEC, K_LZ4, K_LANE, K_N };
+    static pthread_mutex_t mu = PTHREAD_MUTEX_INITIALIZER;
+    static int occ[64][K_N], have[64];
+    int per_sm = 0;
+#define CKC(call)                                                                                      \
+    do {                                                                                               \
+        cudaError_t e_ = (call);                                                                       \
+        if (e_ != cudaSuccess) {                                                                       \
+            snprintf(err, errlen, "%s: %s", #call, cudaGetErrorString(e_));                            \
+            pthread_mutex_unlock(&mu);                                                                 \
+            return -1;                                                                                 \
+        }                                                                                              \
+    } while (0)
+    pthread_mutex_lock(&mu);
+    const int di = cx->device & 63;
+    if (!have[di]) {
+        CKC(cudaFuncSetAttribute(zsk_zstd_fse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ZSK_ZFSE_SMEM));
+        CKC(cudaFuncSetAttribute(zsk_zstd_huf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ZSK_ZHUF_SMEM));
+        CKC(cudaFuncSetAttribute(zsk_zstd_exec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ZSK_ZX_SMEM));
+        CKC(cudaFuncSetAttribute(zsk_zstd_huf_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        CKC(cudaFuncSetAttribute(zsk_zstd_exec_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        CKC(cudaFuncSetAttribute(zsk_lz4_decode_lane_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ZSK_LZ4L_SMEM));
+        CKC(cudaFuncSetAttribute(zsk_lz4_decode_lane_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        CKC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[di][K_ZSTD], zsk_zstd_decode_kernel, ZSK_ZSTD_CTA_THREADS, 0));
+        CKC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[di][K_FSE], zsk_zstd_fse_kernel, ZSK_ZFSE_THREADS, ZSK_ZFSE_SMEM));
+        CKC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[di][K_HUF], zsk_zstd_huf_kernel, 32, ZSK_ZHUF_SMEM));
+        CKC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[di][K_EXEC], zsk_zstd_exec_kernel, 32, ZSK_ZX_SMEM));
+        CKC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[di][K_LZ4], zsk_lz4_decode_batch_kernel, ZSK_LZ4_CTA_THREADS, 0));
+        CKC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[di][K_LANE], zsk_lz4_decode_lane_kernel, ZSK_LZ4L_THREADS, ZSK_LZ4L_SMEM));
+        for (int k = 0; k < K_N; k++)
+            if (occ[di][k] < 1) occ[di][k] = 1;
+        have[di] = 1;
+    }
+    int o[K_N];
+    memcpy(o, occ[di], sizeof(o));
+    pthread_mutex_unlock(&mu);
+#undef CKC
+    per_sm = o[K_ZSTD];
+    if (const char *g = getenv("ZSEEK_B200_ZSTD_CTAS_PER_SM")) { /* tuning knob: resident zstd CTAs per SM */
+        int v = atoi(g);
+        if (v >= 1 && v < per_sm) per_sm = v;
+    }
+    cx->zstd_ctas = per_sm * cx->sm_count;
+    cx->zstd_legacy = 0;
+    if (const char *g = getenv("ZSEEK_B200_ZSTD_LEGACY")) cx->zstd_legacy = atoi(g);
+    cx->zwave_bytes = (uint64_t)4096 << 20;
+    if (const char *g = getenv("ZSEEK_B200_ZSTD_WAVE_MB")) {
+        const unsigned long long v = strtoull(g, NULL, 10);
+        if (v >= 1) cx->zwave_bytes = (uint64_t)v << 20;
+    }
+    cx->zfse_ctas = o[K_FSE] * cx->sm_count;
+    cx->zhuf_ctas = o[K_HUF] * cx->sm_count;
+    per_sm = o[K_EXEC];
+    if (const char *g = getenv("ZSEEK_B200_ZEXEC_CTAS_PER_SM")) { /* tuning knob: resident executor warps per SM */
+        int v = atoi(g);
+        if (v >= 1 && v < per_sm) per_sm = v;
+    }
+    cx->zexec_ctas = per_sm * cx->sm_count;
+    per_sm = o[K_LZ4];
+    if (const char *g = getenv("ZSEEK_B200_LZ4_CTAS_PER_SM")) { /* tuning knob: resident LZ4 CTAs per SM */
+        int v = atoi(g);
+        if (v >= 1 && v < per_sm) per_sm = v;
+    }
+    cx->lz4_ctas = per_sm * cx->sm_count;
+    /* lane-per-frame kernel: wins once there are enough frames to fill the lanes of the GPU (one frame per lane
+     * runs ~10x slower than one frame per warp, but 32x more of them run at once) */
+    per_sm = o[K_LANE];
+    if (const char *g = getenv("ZSEEK_B200_LZ4_LANE_CTAS_PER_SM")) {
+        int v = atoi(g);
+        if (v >= 1 && v < per_sm) per_sm = v;
+    }
+    cx->lz4_lane_ctas = per_sm * cx->sm_count;
+    cx->lz4_lane_min = 40960;             /* measured crossover: 32,768 frames 11.6 ms (warp per frame) vs 14.1 ms (lane per frame), 49,152 frames 18.6 vs 15.9 ms */
+    if (const char *g = getenv("ZSEEK_B200_LZ4_LANE_MIN")) cx->lz4_lane_min = (unsigned)strtoul(g, NULL, 10); /* 0 = always, huge = never */
+    const int trace = getenv("ZSEEK_B200_TRACE") ? atoi(getenv("ZSEEK_B200_TRACE")) : 0;
+    if (trace && !cx->trace_ready) {
+        for (int i = 0; i < ZSK_NTRACE; i++)
+            if (cudaEventCreate(&cx->trace_ev[i]) != cudaSuccess) {
+                snprintf(err, errlen, "cudaEventCreate failed");
+                return -1;
+            }
+        cx->trace_ready = 1;
+    }
+    cx->trace = trace;
+    return 0;
+}
+
+/* a parked context goes to a new reader: knobs re-read, per-reader statistics and the caller's stream forgotten */
+int zsk_cuda_ctx_reuse(zsk_cuda_ctx *cx)
+{
+    cx->streams[ZSK_STREAM_USER] = NULL;
+    cx->launches = 0;
+    cx->k_valid = 0;
+    cx->k_name = NULL;
+    cx->trace_n = 0;
+    CK(cx, cudaSetDevice(cx->device));
+    return ctx_configure(cx, cx->err, sizeof(cx->err));
+}
+
+/* gives back the scratch pools of a context that is being parked when they hold more than max_bytes */
+void zsk_cuda_ctx_trim(zsk_cuda_ctx *cx, size_t max_bytes)
+{
+    cudaSetDevice(cx->device);
+    const size_t held = cx->zblocks_cap * sizeof(zsk_zblock) + cx->zseqs_cap * 3 * sizeof(uint32_t) + cx->zlits_cap +
+                        cx->zjobs_cap * (sizeof(zsk_zframe) + sizeof(uint32_t)) + cx->zbprog_cap * 2 * sizeof(uint32_t);
+    if (held <= max_bytes) return;
+    void *pools[] = { cx->zbprog, cx->zframes, cx->zdeferred, cx->zblocks, cx->zseqs, cx->zlits };
+    for (size_t i = 0; i < sizeof(pools) / sizeof(pools[0]); i++)
+        if (pools[i]) cudaFreeAsync(pools[i], cx->alloc_stream);
+    cx->zbprog = NULL; cx->zframes = NULL; cx->zdeferred = NULL; cx->zblocks = NULL; cx->zseqs = NULL; cx->zlits = NULL;
+    cx->zjobs_cap = cx->zbprog_cap = cx->zblocks_cap = cx->zseqs_cap = cx->zlits_cap = 0;
+}
+
 int zsk_cuda_ctx_create(int device, zsk_cuda_ctx **out, char *err, size_t errlen)
 {
+    /* Every reader brings three streams, and callers keep one reader per thread: with the default 8 hardware work queues
+     * the streams of different readers share queues and wait for each other's events.  Only effective when this library
+     * initialises CUDA in the process; an explicit setting of the caller is left alone. */
+    setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0) {
         snprintf(err, errlen, "no CUDA device: %s", e != cudaSuccess ? cudaGetErrorString(e) : "count is 0");
         return -1;
     }
-    if (device < 0) {
-        const char *s = getenv("ZSEEK_B200_DEVICE");
-        if (!s) s = getenv("LOCAL_RANK");
-        if (s) device = atoi(s) % ndev;
-        else if (cudaGetDevice(&device) != cudaSuccess) device = 0;
-    }
+    if (device < 0) device = zsk_cuda_pick_device();
     if (device >= ndev) {
         snprintf(err, errlen, "CUDA device %d out of range (%d present)", device, ndev);
         return -1;
@@ -104,14 +250,15 @@ int zsk_cuda_ctx_create(int device, zsk_cuda_ctx **out, char *err, size_t errlen
         }                                                                                              \
     } while (0)
     CK0(cudaSetDevice(device));
-    cudaDeviceProp prop;
-    CK0(cudaGetDeviceProperties(&prop, device));
-    if (prop.major < 10) {
-        snprintf(err, errlen, "device %d is sm_%d%d; this library ships sm_100a code only", device, prop.major, prop.minor);
+    int cc_major = 0, cc_minor = 0;
+    CK0(cudaDeviceGetAttribute(&cc_major, cudaDevAttrComputeCapabilityMajor, device));
+    CK0(cudaDeviceGetAttribute(&cc_minor, cudaDevAttrComputeCapabilityMinor, device));
+    if (cc_major < 10) {
+        snprintf(err, errlen, "device %d is sm_%d%d; this library ships sm_100a code only", device, cc_major, cc_minor);
         free(cx);
         return -1;
     }
-    cx->sm_count = prop.multiProcessorCount;
+    CK0(cudaDeviceGetAttribute(&cx->sm_count, cudaDevAttrMultiProcessorCount, device));
     for (int i = 0; i < ZSK_NSTREAMS; i++) CK0(cudaStreamCreateWithFlags(&cx->streams[i], cudaStreamNonBlocking));
     CK0(cudaStreamCreateWithFlags(&cx->alloc_stream, cudaStreamNonBlocking));
     {
@@ -130,60 +277,12 @@ int zsk_cuda_ctx_create(int device, zsk_cuda_ctx **out, char *err, size_t errlen
     CK0(cudaEventCreateWithFlags(&cx->k0, cudaEventBlockingSync));
     CK0(cudaEventCreateWithFlags(&cx->k1, cudaEventBlockingSync));
     CK0(cudaMallocAsync((void **)&cx->counters, ZSK_NCOUNTERS * sizeof(uint32_t), cx->alloc_stream));
-    int per_sm = 0;
-    CK0(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, zsk_zstd_decode_kernel, ZSK_ZSTD_CTA_THREADS, 0));
-    if (per_sm < 1) per_sm = 1;
-    if (const char *g = getenv("ZSEEK_B200_ZSTD_CTAS_PER_SM")) { /* tuning knob: resident zstd CTAs per SM */
-        int v = atoi(g);
-        if (v >= 1 && v < per_sm) per_sm = v;
-    }
-    cx->zstd_ctas = per_sm * cx->sm_count;
-    if (const char *g = getenv("ZSEEK_B200_ZSTD_LEGACY")) cx->zstd_legacy = atoi(g);
-    cx->zwave_bytes = (uint64_t)4096 << 20;
-    if (const char *g = getenv("ZSEEK_B200_ZSTD_WAVE_MB")) {
-        const unsigned long long v = strtoull(g, NULL, 10);
-        if (v >= 1) cx->zwave_bytes = (uint64_t)v << 20;
-    }
-    CK0(cudaFuncSetAttribute(zsk_zstd_fse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ZSK_ZFSE_SMEM));
-    CK0(cudaFuncSetAttribute(zsk_zstd_huf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ZSK_ZHUF_SMEM));
-    CK0(cudaFuncSetAttribute(zsk_zstd_exec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ZSK_ZX_SMEM));
-    CK0(cudaFuncSetAttribute(zsk_zstd_huf_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    CK0(cudaFuncSetAttribute(zsk_zstd_exec_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    CK0(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, zsk_zstd_fse_kernel, ZSK_ZFSE_THREADS, ZSK_ZFSE_SMEM));
-    cx->zfse_ctas = (per_sm < 1 ? 1 : per_sm) * cx->sm_count;
-    CK0(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, zsk_zstd_huf_kernel, 32, ZSK_ZHUF_SMEM));
-    cx->zhuf_ctas = (per_sm < 1 ? 1 : per_sm) * cx->sm_count;
-    CK0(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, zsk_zstd_exec_kernel, 32, ZSK_ZX_SMEM));
-    if (const char *g = getenv("ZSEEK_B200_ZEXEC_CTAS_PER_SM")) { /* tuning knob: resident executor warps per SM */
-        int v = atoi(g);
-        if (v >= 1 && v < per_sm) per_sm = v;
-    }
-    cx->zexec_ctas = (per_sm < 1 ? 1 : per_sm) * cx->sm_count;
     CK0(cudaMallocAsync((void **)&cx->zctr, ZSK_NCOUNTERS * ZSK_ZC_N * sizeof(unsigned long long), cx->alloc_stream));
     CK0(cudaStreamSynchronize(cx->alloc_stream));
-    CK0(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, zsk_lz4_decode_batch_kernel, ZSK_LZ4_CTA_THREADS, 0));
-    if (per_sm < 1) per_sm = 1;
-    if (const char *g = getenv("ZSEEK_B200_LZ4_CTAS_PER_SM")) { /* tuning knob: resident LZ4 CTAs per SM */
-        int v = atoi(g);
-        if (v >= 1 && v < per_sm) per_sm = v;
+    if (ctx_configure(cx, err, errlen)) {
+        free(cx);
+        return -1;
     }
-    cx->lz4_ctas = per_sm * cx->sm_count;
-    /* lane-per-frame kernel: wins once there are enough frames to fill the lanes of the GPU (one frame per lane
-     * runs ~10x slower than one frame per warp, but 32x more of them run at once) */
-    CK0(cudaFuncSetAttribute(zsk_lz4_decode_lane_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ZSK_LZ4L_SMEM));
-    CK0(cudaFuncSetAttribute(zsk_lz4_decode_lane_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    CK0(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, zsk_lz4_decode_lane_kernel, ZSK_LZ4L_THREADS, ZSK_LZ4L_SMEM));
-    if (per_sm < 1) per_sm = 1;
-    if (const char *g = getenv("ZSEEK_B200_LZ4_LANE_CTAS_PER_SM")) {
-        int v = atoi(g);
-        if (v >= 1 && v < per_sm) per_sm = v;
-    }
-    cx->lz4_lane_ctas = per_sm * cx->sm_count;
-    cx->lz4_lane_min = 40960;             /* measured crossover: 32,768 frames 11.6 ms (warp per frame) vs 14.1 ms (lane per frame), 49,152 frames 18.6 vs 15.9 ms */
-    if (const char *g = getenv("ZSEEK_B200_LZ4_LANE_MIN")) cx->lz4_lane_min = (unsigned)strtoul(g, NULL, 10); /* 0 = always, huge = never */
-    if (const char *g = getenv("ZSEEK_B200_TRACE")) cx->trace = atoi(g);
-    if (cx->trace)
-        for (int i = 0; i < ZSK_NTRACE; i++) CK0(cudaEventCreate(&cx->trace_ev[i]));
 #undef CK0
     *out = cx;
     return 0;
@@ -255,9 +354,11 @@ size_t zsk_cuda_free_memory(zsk_cuda_ctx *cx)
  */
 int zsk_cuda_malloc(zsk_cuda_ctx *cx, void **p, size_t n)
 {
+    const double t0 = zsk_dbg() ? zsk_now_ms() : 0;
     CK(cx, cudaSetDevice(cx->device));
     CK(cx, cudaMallocAsync(p, n ? n : 1, cx->alloc_stream));
     CK(cx, cudaStreamSynchronize(cx->alloc_stream));
+    if (zsk_dbg() && zsk_now_ms() - t0 > 0.5) fprintf(stderr, "[zsk cx %p] device alloc %zu bytes: %.2f ms\n", (void *)cx, n, zsk_now_ms() - t0);
     return 0;
 }
 
@@ -270,29 +371,37 @@ int zsk_cuda_free(zsk_cuda_ctx *cx, void *p)
 }
 
 /*
- * Pinned host memory is expensive to create (page pinning under a process-wide driver lock), and readers come and go:
- * buffers are rounded up to a power of two and recycled through a small process-wide free list (at most
- * ZSK_PIN_CACHE_BYTES stay cached).
+ * Pinned host memory is expensive to create (page pinning under a process-wide driver lock: ~0.6-1.5 GB/s on the boxes
+ * measured, and every other CUDA call of the process waits meanwhile), and readers come and go: buffers are rounded up to
+ * a size class (powers of two and 1.5 x powers of two) and recycled through a process-wide free list; at most
+ * ZSEEK_B200_PIN_CACHE_MB (default 6144) stay cached.  The class of a live buffer is kept in a side table, not in a header
+ * in front of the bytes (a header pushed every power-of-two request into the next class: 64 MiB asked, 128 MiB pinned).
  */
-#define ZSK_PIN_CLASSES 40
-#define ZSK_PIN_CACHE_BYTES ((size_t)2 << 30)
-#define ZSK_PIN_HDR 64
+#define ZSK_PIN_CLASSES 80
+#define ZSK_PIN_LIVE 4096
 struct zsk_pin_node { zsk_pin_node *next; };
 static pthread_mutex_t g_pin_mu = PTHREAD_MUTEX_INITIALIZER;
 static zsk_pin_node *g_pin_free[ZSK_PIN_CLASSES];
-static size_t g_pin_cached;
+static size_t g_pin_cached, g_pin_cache_max;
+static struct { void *p; int c; } g_pin_live[ZSK_PIN_LIVE];
+
+static size_t pin_class_bytes(int c) { return ((size_t)2 + (size_t)(c & 1)) << (11 + c / 2); } /* 4K, 6K, 8K, 12K, 16K ... */
 
 static int pin_class(size_t n)
 {
-    int c = 12; /* 4 KiB */
-    while (c < ZSK_PIN_CLASSES - 1 && ((size_t)1 << c) < n) c++;
+    int c = 0;
+    while (c < ZSK_PIN_CLASSES - 1 && pin_class_bytes(c) < n) c++;
     return c;
 }
 
 int zsk_cuda_malloc_host(zsk_cuda_ctx *cx, void **p, size_t n)
 {
-    const int c = pin_class(n + ZSK_PIN_HDR);
-    const size_t bytes = (size_t)1 << c;
+    const int c = pin_class(n ? n : 1);
+    const size_t bytes = pin_class_bytes(c);
+    if (bytes < n) {
+        snprintf(cx->err, sizeof(cx->err), "pinned allocation too large");
+        return -1;
+    }
     pthread_mutex_lock(&g_pin_mu);
     zsk_pin_node *nd = g_pin_free[c];
     if (nd) {
@@ -301,24 +410,43 @@ int zsk_cuda_malloc_host(zsk_cuda_ctx *cx, void **p, size_t n)
     }
     pthread_mutex_unlock(&g_pin_mu);
     if (!nd) {
+        const double t0 = zsk_dbg() ? zsk_now_ms() : 0;
         CK(cx, cudaSetDevice(cx->device));
         void *raw = NULL;
         CK(cx, cudaHostAlloc(&raw, bytes, cudaHostAllocPortable));
         nd = (zsk_pin_node *)raw;
+        if (zsk_dbg()) fprintf(stderr, "[zsk cx %p] pinned alloc %zu bytes (asked %zu): %.2f ms\n", (void *)cx, bytes, n, zsk_now_ms() - t0);
     }
-    *(int *)((char *)nd + 8) = c; /* the class lives in the header in front of the caller's bytes */
-    *p = (char *)nd + ZSK_PIN_HDR;
+    pthread_mutex_lock(&g_pin_mu);
+    int slot = -1;
+    for (int i = 0; i < ZSK_PIN_LIVE; i++)
+        if (!g_pin_live[i].p) { slot = i; break; }
+    if (slot >= 0) { g_pin_live[slot].p = nd; g_pin_live[slot].c = c; }
+    pthread_mutex_unlock(&g_pin_mu);
+    if (slot < 0) { /* more live pinned buffers than the table holds: not recyclable, still usable */
+        cudaFreeHost(nd);
+        snprintf(cx->err, sizeof(cx->err), "too many pinned buffers");
+        return -1;
+    }
+    *p = nd;
     return 0;
 }
 
 int zsk_cuda_free_host(zsk_cuda_ctx *cx, void *p)
 {
     if (!p) return 0;
-    zsk_pin_node *nd = (zsk_pin_node *)((char *)p - ZSK_PIN_HDR);
-    const int c = *(int *)((char *)nd + 8);
-    const size_t bytes = (size_t)1 << c;
+    zsk_pin_node *nd = (zsk_pin_node *)p;
     pthread_mutex_lock(&g_pin_mu);
-    const bool keep = g_pin_cached + bytes <= ZSK_PIN_CACHE_BYTES;
+    if (!g_pin_cache_max) {
+        const char *g = getenv("ZSEEK_B200_PIN_CACHE_MB");
+        g_pin_cache_max = (g && *g ? (size_t)strtoull(g, NULL, 10) : (size_t)6144) << 20;
+        if (!g_pin_cache_max) g_pin_cache_max = 1;
+    }
+    int c = -1;
+    for (int i = 0; i < ZSK_PIN_LIVE; i++)
+        if (g_pin_live[i].p == p) { c = g_pin_live[i].c; g_pin_live[i].p = NULL; break; }
+    const size_t bytes = c >= 0 ? pin_class_bytes(c) : 0;
+    const bool keep = c >= 0 && g_pin_cached + bytes <= g_pin_cache_max;
     if (keep) {
         nd->next = g_pin_free[c];
         g_pin_free[c] = nd;
@@ -405,6 +533,7 @@ static int next_counter(zsk_cuda_ctx *cx, int stream, uint32_t **out)
 static int grow_pool(zsk_cuda_ctx *cx, void **p, size_t *cap_bytes, size_t need)
 {
     if (need <= *cap_bytes) return 0;
+    const double t0 = zsk_dbg() ? zsk_now_ms() : 0;
     size_t want = need > 2 * *cap_bytes ? need : 2 * *cap_bytes;
     /* the pools are shared by every launch of this context: the launches in flight must be through with them */
     for (int i = 0; i < ZSK_NSTREAMS; i++) CK(cx, cudaStreamSynchronize(cx->streams[i]));
@@ -419,6 +548,7 @@ static int grow_pool(zsk_cuda_ctx *cx, void **p, size_t *cap_bytes, size_t need)
     }
     CK(cx, cudaStreamSynchronize(cx->alloc_stream));
     *cap_bytes = want;
+    if (zsk_dbg()) fprintf(stderr, "[zsk cx %p] scratch pool grown to %zu bytes: %.2f ms\n", (void *)cx, want, zsk_now_ms() - t0);
     return 0;
 }
 

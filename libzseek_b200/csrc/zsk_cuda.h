@@ -22,6 +22,10 @@ enum { ZSK_H2D = 1, ZSK_D2H = 2, ZSK_D2D = 3 };
 /* device < 0: take ZSEEK_B200_DEVICE, else LOCAL_RANK, else the current CUDA device */
 int zsk_cuda_ctx_create(int device, zsk_cuda_ctx **out, char *err, size_t errlen);
 void zsk_cuda_ctx_destroy(zsk_cuda_ctx *cx);
+/* contexts of closed readers are parked and handed to later readers of the same device (reader.c) */
+int zsk_cuda_pick_device(void);                               /* the device zsk_cuda_ctx_create(-1, ...) would take; -1: none */
+int zsk_cuda_ctx_reuse(zsk_cuda_ctx *cx);                     /* re-reads the tuning knobs, forgets per-reader statistics */
+void zsk_cuda_ctx_trim(zsk_cuda_ctx *cx, size_t max_bytes);   /* frees the scratch pools when they hold more than max_bytes */
 const char *zsk_cuda_error(zsk_cuda_ctx *cx);
 int zsk_cuda_device(const zsk_cuda_ctx *cx);
 int zsk_cuda_sm_count(const zsk_cuda_ctx *cx);

@@ -15,7 +15,7 @@ def child(lib, path, T):
     ent = np.frombuffer(image, dtype="<u4", count=2 * n, offset=len(image) - (8 + 8 * n + 9) + 8).reshape(n, 2)
     total = int(ent[:, 1].astype(np.uint64).sum())
     nb = C.c_uint64()
-    for rep in range(2):
+    for rep in range(int(os.environ.get("REPS", "3"))):
         t0 = time.time()
         t = L.refdrive_scan(image.ctypes.data, image.size, total, T, 4096, 1, 1, None, C.byref(nb))
         print(f"rep {rep}: harness {t:.3f} s ({total / t / 1e9:.2f} GB/s), wall incl. open/close {time.time() - t0:.3f} s", flush=True)
