@@ -63,6 +63,7 @@ struct zseek_reader {
     /* device */
     zsk_cuda_ctx *cx;
     uint64_t *g_coff, *g_doff;
+    size_t parked_bytes; /* device memory this reader held when it was parked */
     size_t n_cap;      /* entries g_coff / g_doff / g_frame_src hold */
     size_t slab_bytes; /* bytes of g_slab */
 
@@ -141,6 +142,7 @@ struct zseek_reader {
     /* read-ahead */
     uint64_t ra_next;
     uint32_t ra_window, ra_max;
+    uint32_t ra_cap; /* largest read-ahead window (frames) this reader uses; 0 = not decided yet (ra_limit) */
     size_t chunk_bytes; /* decoded bytes per pipeline stage of host-destination range reads */
     size_t ramp_bytes;  /* size of the first pipeline stage; stages double until they reach chunk_bytes */
     /* launches of at least sort_min LZ4 frames (sort_min_zstd zstd frames) hand the kernel a job list ordered by
@@ -170,6 +172,7 @@ static atomic_size_t g_resident_bytes;
 static pthread_mutex_t g_park_mu = PTHREAD_MUTEX_INITIALIZER;
 static struct zseek_reader *g_parked[ZSK_MAX_PARKED];
 static int g_nparked;
+static size_t g_parked_bytes; /* device memory the parked readers hold; at most ZSEEK_B200_PARK_MB (default 8192) */
 
 /* ------------------------------------------------------------------ errors (reference src/common.c:45-54) */
 static bool stream_frames_finish(zseek_reader_t *r, uint64_t lo, uint64_t hi, bool resident, bool ok, char *errbuf);
@@ -558,15 +561,22 @@ static bool ensure_stage(zseek_reader_t *r, size_t bytes, char *errbuf)
 
 /* most frames an ordinary read-ahead window may hold right now: the reader's own maximum, cut down so that the two pinned
  * windows of every live reader of the process fit ZSEEK_B200_WINDOW_BUDGET_MB (default 2048) together */
-static uint32_t ra_limit(const zseek_reader_t *r)
+static uint32_t ra_limit(zseek_reader_t *r)
 {
     static size_t budget;
     if (!budget)
         budget = MAX(env_size("ZSEEK_B200_WINDOW_BUDGET_MB", 2048), 1) << 20;
-    const unsigned live = MAX(atomic_load(&g_live_readers), 1u);
-    const size_t per_window = MAX(budget / (2 * (size_t)live), (size_t)8 << 20);
-    const size_t frames = per_window / MAX((size_t)r->max_dsize, 1);
-    return (uint32_t)MAX(1, MIN((size_t)r->ra_max, frames));
+    if (!r->ra_cap) {
+        /* decided once per reader, when its scan first grows a window, and rounded down to a power of two: the pinned
+         * windows of the readers of a thread pool then come in one size and are recycled from scan to scan */
+        const unsigned live = MAX(atomic_load(&g_live_readers), 1u);
+        size_t per_window = (size_t)8 << 20;
+        while (per_window * 2 <= budget / (2 * (size_t)live))
+            per_window *= 2;
+        const size_t frames = per_window / MAX((size_t)r->max_dsize, 1);
+        r->ra_cap = (uint32_t)MAX(1, MIN((size_t)r->ra_max, frames));
+    }
+    return r->ra_cap;
 }
 
 /* pinned window `which` of at least `bytes` (grown geometrically up to window_cap: a reader that only ever sees small
@@ -872,7 +882,7 @@ static bool reader_park(zseek_reader_t *r)
         return false;
     reader_quiesce(r);
     free_file_state(r);
-    const size_t keep_max = (size_t)256 << 20;
+    const size_t keep_max = ((size_t)512 << 20) + 4096;
     /* buffers whose size depends on the file's frame geometry in ways the next file need not share, and the big ones */
     void *drop[] = { r->g_touched, r->g_bslab, r->g_bjob_ids, r->g_bjob_limits, r->g_bctl, r->g_bjob_offs, r->g_bjob_status, r->g_bsrc,
                      r->g_comp_cap > keep_max ? r->g_comp : NULL, r->g_out_cap > keep_max ? r->g_out : NULL,
@@ -898,12 +908,18 @@ static bool reader_park(zseek_reader_t *r)
     k.g_b_offsets = r->g_b_offsets; k.g_b_counts = r->g_b_counts; k.g_b_dstoffs = r->g_b_dstoffs;
     k.g_b_frame = r->g_b_frame; k.g_b_inframe = r->g_b_inframe; k.g_b_nbytes = r->g_b_nbytes;
     zsk_cuda_ctx_trim(k.cx, keep_max);
+    k.parked_bytes = k.g_comp_cap + k.g_out_cap + k.slab_bytes + 24 * k.n_cap + zsk_cuda_ctx_held(k.cx);
     pthread_mutex_destroy(&r->lock);
     *r = k;
+    static size_t park_max;
+    if (!park_max)
+        park_max = MAX(env_size("ZSEEK_B200_PARK_MB", 8192), 1) << 20;
     pthread_mutex_lock(&g_park_mu);
-    const bool parked = g_nparked < ZSK_MAX_PARKED;
-    if (parked)
+    const bool parked = g_nparked < ZSK_MAX_PARKED && g_parked_bytes + r->parked_bytes <= park_max;
+    if (parked) {
         g_parked[g_nparked++] = r;
+        g_parked_bytes += r->parked_bytes;
+    }
     pthread_mutex_unlock(&g_park_mu);
     if (!parked)
         pthread_mutex_init(&r->lock, NULL); /* reader_free destroys it */
@@ -922,6 +938,7 @@ static zseek_reader_t *reader_new(void)
         if (zsk_cuda_device(g_parked[i]->cx) == dev) {
             r = g_parked[i];
             g_parked[i] = g_parked[--g_nparked];
+            g_parked_bytes -= r->parked_bytes;
             break;
         }
     pthread_mutex_unlock(&g_park_mu);

@@ -123,6 +123,9 @@ static int ctx_configure(zsk_cuda_ctx *cx, char *err, size_t errlen)
         CKC(cudaFuncSetAttribute(zsk_zstd_fse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ZSK_ZFSE_SMEM));
         CKC(cudaFuncSetAttribute(zsk_zstd_huf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ZSK_ZHUF_SMEM));
         CKC(cudaFuncSetAttribute(zsk_zstd_exec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ZSK_ZX_SMEM));
+#ifdef ZSK_EXP_FSE_CARVEOUT
+        CKC(cudaFuncSetAttribute(zsk_zstd_fse_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, ZSK_EXP_FSE_CARVEOUT));
+#endif
         CKC(cudaFuncSetAttribute(zsk_zstd_huf_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         CKC(cudaFuncSetAttribute(zsk_zstd_exec_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         CKC(cudaFuncSetAttribute(zsk_lz4_decode_lane_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ZSK_LZ4L_SMEM));
@@ -203,13 +206,19 @@ int zsk_cuda_ctx_reuse(zsk_cuda_ctx *cx)
     return ctx_configure(cx, cx->err, sizeof(cx->err));
 }
 
+/* device bytes of the scratch pools a context holds */
+size_t zsk_cuda_ctx_held(const zsk_cuda_ctx *cx)
+{
+    return cx->zblocks_cap * sizeof(zsk_zblock) + cx->zseqs_cap * 3 * sizeof(uint32_t) + cx->zlits_cap +
+           cx->zjobs_cap * (sizeof(zsk_zframe) + sizeof(uint32_t)) + cx->zbprog_cap * 2 * sizeof(uint32_t) +
+           (cx->scratch ? (size_t)cx->sm_count * ZSK_LIT_SCRATCH : 0);
+}
+
 /* gives back the scratch pools of a context that is being parked when they hold more than max_bytes */
 void zsk_cuda_ctx_trim(zsk_cuda_ctx *cx, size_t max_bytes)
 {
     cudaSetDevice(cx->device);
-    const size_t held = cx->zblocks_cap * sizeof(zsk_zblock) + cx->zseqs_cap * 3 * sizeof(uint32_t) + cx->zlits_cap +
-                        cx->zjobs_cap * (sizeof(zsk_zframe) + sizeof(uint32_t)) + cx->zbprog_cap * 2 * sizeof(uint32_t);
-    if (held <= max_bytes) return;
+    if (zsk_cuda_ctx_held(cx) <= max_bytes) return;
     void *pools[] = { cx->zbprog, cx->zframes, cx->zdeferred, cx->zblocks, cx->zseqs, cx->zlits };
     for (size_t i = 0; i < sizeof(pools) / sizeof(pools[0]); i++)
         if (pools[i]) cudaFreeAsync(pools[i], cx->alloc_stream);
@@ -572,7 +581,7 @@ static int launch_zstd_pipeline(zsk_cuda_ctx *cx, zsk_decode_args a, cudaStream_
     /* pool sizes for typical data: one block per 2 KiB of output, one sequence (12 bytes of records) per 5 bytes, 3/4 of the output as
      * Huffman literals; frames beyond that are deferred to the old kernel by P0 */
     const size_t want_blocks = (size_t)(dsum / 2048) + 4 * njobs + 64;
-    const size_t want_seqs = (size_t)(dsum / 5) + 64 * njobs + 1024;
+    const size_t want_seqs = (size_t)(dsum / 5) + 64 * njobs + 8 * want_blocks + 1024; /* a block's arrays are padded to 8 sequences */
     const size_t want_lits = (size_t)(dsum / 4 * 3) + 64 * njobs + 4096;
     size_t cap_b = cx->zblocks_cap * sizeof(zsk_zblock), cap_s = cx->zseqs_cap * 3 * sizeof(uint32_t), cap_l = cx->zlits_cap ? cx->zlits_cap + ZSK_PAD_BACK : 0;
     if ((rc = grow_pool(cx, (void **)&cx->zblocks, &cap_b, want_blocks * sizeof(zsk_zblock)))) return rc;

@@ -26,6 +26,7 @@ void zsk_cuda_ctx_destroy(zsk_cuda_ctx *cx);
 int zsk_cuda_pick_device(void);                               /* the device zsk_cuda_ctx_create(-1, ...) would take; -1: none */
 int zsk_cuda_ctx_reuse(zsk_cuda_ctx *cx);                     /* re-reads the tuning knobs, forgets per-reader statistics */
 void zsk_cuda_ctx_trim(zsk_cuda_ctx *cx, size_t max_bytes);   /* frees the scratch pools when they hold more than max_bytes */
+size_t zsk_cuda_ctx_held(const zsk_cuda_ctx *cx);            /* device bytes of the scratch pools */
 const char *zsk_cuda_error(zsk_cuda_ctx *cx);
 int zsk_cuda_device(const zsk_cuda_ctx *cx);
 int zsk_cuda_sm_count(const zsk_cuda_ctx *cx);

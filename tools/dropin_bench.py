@@ -40,18 +40,23 @@ def child(lib, path, threads):
             if shared and T == 1:
                 continue
             key = f"T{T}_{'shared_reader' if shared else 'reader_per_thread'}"
-            best = None
-            for _ in range(2):
+            # best of three passes for both libraries; every pass opens fresh readers (libzseek_b200 hands a new reader the
+            # device state of a closed one, so its first pass is the cold-process figure and the later ones the steady state)
+            times = []
+            for _ in range(3):
                 t = L.refdrive_scan(image.ctypes.data, image.size, total, T, 4096, 1, 1, None, C.byref(nbytes))
                 assert t > 0 and nbytes.value == total, t
-                best = t if best is None else min(best, t)
-            out.setdefault("scan_4k_GBps", {})[key] = round(total / best / 1e9, 3)
+                times.append(t)
+            out.setdefault("scan_4k_GBps", {})[key] = round(total / min(times) / 1e9, 3)
+            out.setdefault("scan_4k_GBps_first_pass", {})[key] = round(total / times[0] / 1e9, 3)
             offs = rng.integers(0, total - 4096, 200000 if T > 1 else 20000, dtype=np.uint64)
-            # warm-up pass on the same reader population is not possible (readers are per call): the figure includes whatever
-            # the library does on its first misses
-            t = L.refdrive_random(image.ctypes.data, image.size, offs.ctypes.data, offs.size, 4096, T, 0, 1, None, C.byref(ops))
-            assert t > 0, t
-            out.setdefault("random_4k_ops_per_s", {})[key] = round(ops.value / t)
+            rates = []
+            for _ in range(2):
+                t = L.refdrive_random(image.ctypes.data, image.size, offs.ctypes.data, offs.size, 4096, T, 0, 1, None, C.byref(ops))
+                assert t > 0, t
+                rates.append(ops.value / t)
+            out.setdefault("random_4k_ops_per_s", {})[key] = round(max(rates))
+            out.setdefault("random_4k_ops_per_s_first_pass", {})[key] = round(rates[0])
     print(json.dumps(out))
 
 

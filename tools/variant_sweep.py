@@ -21,14 +21,18 @@ def child(path, rawpath, iters):
         out = torch.empty(rd.size + 64, dtype=torch.uint8, device="cuda")
         rd.load(0, rd.frames)
         ms = []
+        err = ""
         for _ in range(iters):
-            rd.decode_frames(0, rd.frames, out)
+            try:
+                rd.decode_frames(0, rd.frames, out)
+            except Exception as e:  # noqa: BLE001 -- experiment builds may decode garbage on purpose; the kernel time still counts
+                err = f"  [{e}]"
             ms.append(rd.last_decode_ms)
         raw = torch.from_numpy(np.fromfile(rawpath, dtype=np.uint8)).cuda()
         ok = bool(torch.equal(out[:raw.numel()], raw))
         best = min(ms)
         print(f"  {os.path.basename(os.environ.get('ZSEEK_B200_LIB', 'default')):28s} {rd.frames} frames  best {best:8.3f} ms  {rd.size / best / 1e6:7.1f} GB/s  "
-              f"all {[round(m, 2) for m in ms]}  verified {ok}", flush=True)
+              f"all {[round(m, 2) for m in ms]}  verified {ok}{err}", flush=True)
 
 
 def main():
