@@ -83,10 +83,17 @@ template <unsigned N> static __device__ __forceinline__ void zsk_cp_wait() { asm
 static __device__ __forceinline__ void zsk_cp_reset() {}
 #endif
 
-/* eight words to a 32-byte aligned address as ONE 256-bit store (STG.E.256, sm_100), kept out of L1 */
+/* eight words to a 32-byte aligned address as ONE 256-bit store (STG.E.256, sm_100); _cg: kept out of L1 */
 #ifdef ZSK_EMU
 static inline void zsk_st256_cg(uint32_t *p, const uint32_t v[8]) { for (int k = 0; k < 8; k++) p[k] = v[k]; }
+static inline void zsk_st256(uint32_t *p, const uint32_t v[8]) { for (int k = 0; k < 8; k++) p[k] = v[k]; }
 #else
+static __device__ __forceinline__ void zsk_st256(uint32_t *p, const uint32_t v[8])
+{
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]),
+                 "r"(v[6]), "r"(v[7])
+                 : "memory");
+}
 static __device__ __forceinline__ void zsk_st256_cg(uint32_t *p, const uint32_t v[8])
 {
     asm volatile("st.global.cg.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]),

@@ -357,11 +357,18 @@ __global__ void __launch_bounds__(ZSK_LZ4L_THREADS) zsk_lz4_decode_lane_kernel(z
                 if (ope - flushed >= chunk) {
                     if (chunk == 32u) {
                         const uint32_t *fp = &ZSK_L_OW((flushed + oal) >> 2); /* 32-byte aligned: the 8 words do not wrap */
+#ifdef ZSK_LZ4L_SPLIT_FLUSH
                         const uint4 v0 = make_uint4(fp[0], fp[32], fp[64], fp[96]);
                         const uint4 v1 = make_uint4(fp[128], fp[160], fp[192], fp[224]);
                         uint4 *o = (uint4 *)(out + flushed);
                         o[0] = v0;
                         o[1] = v1;
+#else
+                        /* ONE 256-bit store per sector: an SM retires scattered sector writes slowly (~5 cycles each, measured
+                         * on the zstd FSE stage), and 32 lanes write 32 different sectors here */
+                        const uint32_t v[8] = { fp[0], fp[32], fp[64], fp[96], fp[128], fp[160], fp[192], fp[224] };
+                        zsk_st256((uint32_t *)(out + flushed), v);
+#endif
                         flushed += 32u;
                     } else {
                         for (uint32_t i = 0; i < chunk; i++) {
