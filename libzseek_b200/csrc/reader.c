@@ -154,8 +154,20 @@ struct zseek_reader {
 
     /* host/device classification of caller buffers, cached per 2 MiB virtual-address block so that the hot
      * zseek_pread path does not enter the CUDA driver (a global lock) on every call */
-    uintptr_t ptr_block[8];
-    int8_t ptr_is_dev[8];
+    _Atomic uint64_t ptr_cache[8]; /* ((address >> 21) + 1) << 1 | is_device; 0 = empty.  Atomic: the resident fast path reads it without the lock */
+
+    /* Shared readers: once the whole shard sits decoded in the pinned window (resident), host reads are memcpys out of
+     * memory that no longer changes; they take res_lock for reading instead of the reader mutex, so the threads of a pool
+     * that shares one reader copy in parallel (the reference serialises them on its lock, src/decompress.c:387,499). */
+    pthread_rwlock_t res_lock;
+    atomic_bool resident_fast;
+
+    /* residency in HBM: when the pinned budget of the process is spent (one reader per thread over the same file), the shard
+     * is decoded once into device memory instead and every read becomes a small device-to-host copy */
+    uint8_t *g_res;
+    uint8_t *h_bounce; /* pinned, ZSK_BOUNCE bytes: small reads land here first (a copy to pageable memory goes through the driver's own staging and takes ~10x longer when many threads do it at once) */
+    size_t hbm_resident_bytes;
+    bool hbm_resident;
 };
 
 /* Process-wide bookkeeping for callers that keep one reader per thread: pinned host memory is the scarce resource (it is
@@ -163,6 +175,8 @@ struct zseek_reader {
  * of live readers, and whole-shard residency draws from one process-wide budget. */
 static atomic_uint g_live_readers;
 static atomic_size_t g_resident_bytes;
+static atomic_size_t g_hbm_resident_bytes;
+#define ZSK_BOUNCE ((size_t)64 << 10)
 
 /* Closed readers are PARKED, not destroyed: the next zseek_reader_open* of the process takes over the device context (streams,
  * events, the zstd scratch pools), the device buffers and the pinned windows of a parked one.  A caller that opens one
@@ -816,13 +830,13 @@ static bool fill_window(zseek_reader_t *r, uint64_t lo, uint64_t hi, bool mirror
 
 static int buf_on_device(zseek_reader_t *r, const void *buf)
 {
-    const uintptr_t block = ((uintptr_t)buf >> 21) + 1; /* +1: 0 marks an empty cache entry */
+    const uint64_t block = ((uint64_t)(uintptr_t)buf >> 21) + 1; /* +1: 0 marks an empty cache entry */
     const unsigned i = (unsigned)(block & 7);
-    if (r->ptr_block[i] == block)
-        return r->ptr_is_dev[i];
+    const uint64_t e = atomic_load_explicit(&r->ptr_cache[i], memory_order_relaxed);
+    if ((e >> 1) == block)
+        return (int)(e & 1);
     int d = zsk_cuda_pointer_is_device(r->cx, buf);
-    r->ptr_block[i] = block;
-    r->ptr_is_dev[i] = (int8_t)(d > 0);
+    atomic_store_explicit(&r->ptr_cache[i], (block << 1) | (uint64_t)(d > 0), memory_order_relaxed);
     return d > 0;
 }
 
@@ -836,10 +850,13 @@ static bool in_shard(zseek_reader_t *r, uint64_t f, char *errbuf)
 
 /* ------------------------------------------------------------------ open / close */
 /* waits for everything the reader queued and takes it out of the process-wide counts */
+static void drop_resident(zseek_reader_t *r);
 static void reader_quiesce(zseek_reader_t *r)
 {
-    if (r->cx)
+    if (r->cx) {
         prefetch_drop(r);
+        drop_resident(r);
+    }
     if (r->counted)
         atomic_fetch_sub(&g_live_readers, 1u);
     r->counted = false;
@@ -897,6 +914,7 @@ static bool reader_park(zseek_reader_t *r)
     if (r->g_comp_cap <= keep_max) { k.g_comp = r->g_comp; k.g_comp_cap = r->g_comp_cap; }
     if (r->g_out_cap <= keep_max) { k.g_out = r->g_out; k.g_out_cap = r->g_out_cap; }
     k.h_stage = r->h_stage; k.stage_half = r->stage_half;
+    k.h_bounce = r->h_bounce;
     for (int w = 0; w < 2; w++) {
         if (r->mir_cap[w] <= keep_max) { k.h_mir[w] = r->h_mir[w]; k.mir_cap[w] = r->mir_cap[w]; }
         else zsk_cuda_free_host(r->cx, r->h_mir[w]); /* a whole-shard window: back to the pinned cache */
@@ -910,6 +928,7 @@ static bool reader_park(zseek_reader_t *r)
     zsk_cuda_ctx_trim(k.cx, keep_max);
     k.parked_bytes = k.g_comp_cap + k.g_out_cap + k.slab_bytes + 24 * k.n_cap + zsk_cuda_ctx_held(k.cx);
     pthread_mutex_destroy(&r->lock);
+    pthread_rwlock_destroy(&r->res_lock);
     *r = k;
     static size_t park_max;
     if (!park_max)
@@ -921,8 +940,10 @@ static bool reader_park(zseek_reader_t *r)
         g_parked_bytes += r->parked_bytes;
     }
     pthread_mutex_unlock(&g_park_mu);
-    if (!parked)
-        pthread_mutex_init(&r->lock, NULL); /* reader_free destroys it */
+    if (!parked) { /* reader_free destroys them */
+        pthread_mutex_init(&r->lock, NULL);
+        pthread_rwlock_init(&r->res_lock, NULL);
+    }
     return parked;
 }
 
@@ -944,13 +965,16 @@ static zseek_reader_t *reader_new(void)
     pthread_mutex_unlock(&g_park_mu);
     if (r && zsk_cuda_ctx_reuse(r->cx)) { /* the parked context is unusable: start afresh */
         pthread_mutex_init(&r->lock, NULL);
+        pthread_rwlock_init(&r->res_lock, NULL);
         reader_free(r);
         r = NULL;
     }
     if (!r)
         r = calloc(1, sizeof(*r));
-    if (r)
+    if (r) {
         pthread_mutex_init(&r->lock, NULL);
+        pthread_rwlock_init(&r->res_lock, NULL);
+    }
     return r;
 }
 
@@ -965,13 +989,14 @@ static void reader_free(zseek_reader_t *r)
                         r->g_out, r->g_bslab, r->g_bjob_ids, r->g_bjob_limits, r->g_bctl, r->g_bjob_offs, r->g_bjob_status, r->g_bsrc };
         for (size_t i = 0; i < sizeof(dev) / sizeof(dev[0]); i++)
             zsk_cuda_free(r->cx, dev[i]);
-        void *pin[] = { r->h_stage, r->h_mir[0], r->h_mir[1], r->h_job_ids, r->h_job_offs, r->h_job_status, r->h_job_limits };
+        void *pin[] = { r->h_stage, r->h_mir[0], r->h_mir[1], r->h_job_ids, r->h_job_offs, r->h_job_status, r->h_job_limits, r->h_bounce };
         for (size_t i = 0; i < sizeof(pin) / sizeof(pin[0]); i++)
             zsk_cuda_free_host(r->cx, pin[i]);
         zsk_cuda_ctx_destroy(r->cx);
     }
     free_file_state(r);
     pthread_mutex_destroy(&r->lock);
+    pthread_rwlock_destroy(&r->res_lock);
     free(r);
 }
 
@@ -1198,15 +1223,71 @@ static bool go_resident(zseek_reader_t *r, void *call_data)
     r->mir_cur = 0;
     r->mir_lo = r->shard_lo;
     r->mir_hi = r->shard_hi;
+    pthread_rwlock_wrlock(&r->res_lock);
     r->resident = true;
+    pthread_rwlock_unlock(&r->res_lock);
+    atomic_store(&r->resident_fast, true);
+    return true;
+}
+
+/* Decodes the whole shard into device memory (one launch per 4 GiB of compressed input); afterwards the compressed image
+ * and the scratch pools are given back: nothing is decoded again until the shard changes. */
+static bool read_range_device(zseek_reader_t *r, uint8_t *dst, size_t count, size_t offset, void *call_data, char *errbuf);
+static bool go_resident_hbm(zseek_reader_t *r, void *call_data)
+{
+    static size_t budget;
+    if (!budget)
+        budget = MAX(env_size("ZSEEK_B200_RESIDENT_HBM_MB", 32768), 1) << 20;
+    char scratch[ZSEEK_ERRBUF_SIZE];
+    const size_t bytes = (size_t)(r->d_off[r->shard_hi] - r->d_off[r->shard_lo]);
+    if (bytes == 0)
+        return false;
+    if (atomic_fetch_add(&g_hbm_resident_bytes, bytes) + bytes > budget) {
+        atomic_fetch_sub(&g_hbm_resident_bytes, bytes);
+        return false;
+    }
+    r->hbm_resident_bytes = bytes;
+    prefetch_drop(r);
+    /* room for the decoded shard, its compressed image and the scratch of one decode wave */
+    const size_t need = bytes + (size_t)(r->c_off[r->shard_hi] - r->c_off[r->shard_lo]) + 4 * MIN(bytes, (size_t)4 << 30) + ((size_t)1 << 30);
+    if (zsk_cuda_free_memory(r->cx) < need || (!r->h_bounce && zsk_cuda_malloc_host(r->cx, (void **)&r->h_bounce, ZSK_BOUNCE)) ||
+        zsk_cuda_malloc(r->cx, (void **)&r->g_res, bytes + ZSK_PAD_BACK) ||
+        !read_range_device(r, r->g_res, bytes, (size_t)r->d_off[r->shard_lo], call_data, scratch)) {
+        zsk_cuda_free(r->cx, r->g_res);
+        r->g_res = NULL;
+        atomic_fetch_sub(&g_hbm_resident_bytes, r->hbm_resident_bytes);
+        r->hbm_resident_bytes = 0;
+        return false;
+    }
+    r->hbm_resident = true;
+    zsk_cuda_stream_sync(r->cx, ZSK_STREAM_COMPUTE);
+    zsk_cuda_free(r->cx, r->g_comp);
+    r->g_comp = NULL;
+    r->g_comp_cap = 0;
+    r->res_lo = r->res_hi = 0;
+    zsk_cuda_ctx_trim(r->cx, 0);
     return true;
 }
 
 /* back to the ordinary two-half read-ahead window (allocated again on first use) */
 static void drop_resident(zseek_reader_t *r)
 {
+    if (r->hbm_resident) {
+        zsk_cuda_stream_sync(r->cx, ZSK_STREAM_COMPUTE);
+        zsk_cuda_free(r->cx, r->g_res);
+        r->g_res = NULL;
+        r->hbm_resident = false;
+        atomic_fetch_sub(&g_hbm_resident_bytes, r->hbm_resident_bytes);
+        r->hbm_resident_bytes = 0;
+        r->resident_tried = false;
+        r->random_misses = 0;
+    }
     if (!r->resident)
         return;
+    atomic_store(&r->resident_fast, false);
+    pthread_rwlock_wrlock(&r->res_lock); /* readers on the fast path are through with the window */
+    r->resident = false;
+    pthread_rwlock_unlock(&r->res_lock);
     zsk_cuda_free_host(r->cx, r->h_mir[0]);
     r->h_mir[0] = NULL;
     r->mir_cap[0] = 0;
@@ -1234,6 +1315,18 @@ static ssize_t pread_locked(zseek_reader_t *r, void *buf, size_t count, size_t o
     int on_device = buf_on_device(r, buf);
     if (!on_device && f >= r->mir_lo && f < r->mir_hi) { /* pinned window hit: plain memcpy */
         memcpy(buf, mirror_half(r, r->mir_cur) + (offset - r->d_off[r->mir_lo]), n);
+        return (ssize_t)n;
+    }
+    if (r->hbm_resident) { /* the shard sits decoded in HBM: one small copy */
+        const uint8_t *from = r->g_res + (offset - (size_t)r->d_off[r->shard_lo]);
+        const bool bounce = !on_device && n <= ZSK_BOUNCE;
+        if (zsk_cuda_memcpy_async(r->cx, bounce ? (void *)r->h_bounce : buf, from, n, on_device ? ZSK_D2D : ZSK_D2H, ZSK_STREAM_COMPUTE) ||
+            zsk_cuda_stream_sync_spin(r->cx, ZSK_STREAM_COMPUTE)) {
+            cuda_fail(r, errbuf, "copy frame");
+            return -1;
+        }
+        if (bounce)
+            memcpy(buf, r->h_bounce, n);
         return (ssize_t)n;
     }
     if (!on_device && r->pf_active && f == r->pf_lo) {
@@ -1277,6 +1370,8 @@ static ssize_t pread_locked(zseek_reader_t *r, void *buf, size_t count, size_t o
                 memcpy(buf, mirror_half(r, r->mir_cur) + (offset - r->d_off[r->mir_lo]), n);
                 return (ssize_t)n;
             }
+            if (go_resident_hbm(r, call_data)) /* the pinned budget of the process is spent: keep the decoded shard in HBM */
+                return pread_locked(r, buf, count, offset, call_data, errbuf);
         }
         uint64_t hi = MIN(f + (on_device ? MIN(r->ra_window, r->nslots) : r->ra_window), r->shard_hi);
         const bool dbg = getenv("ZSEEK_B200_DEBUG") != NULL;
@@ -1338,6 +1433,29 @@ ssize_t zseek_pread(zseek_reader_t *reader, void *buf, size_t count, size_t offs
     if (!reader) {
         set_error(errbuf, "invalid reader");
         return 0; /* sic: the reference returns `false` here (src/decompress.c:809-812) */
+    }
+    if (atomic_load_explicit(&reader->resident_fast, memory_order_acquire)) {
+        /* resident shard, host buffer: a memcpy under the read lock; everything else takes the ordinary path */
+        ssize_t fast = -2;
+        pthread_rwlock_rdlock(&reader->res_lock);
+        if (reader->resident) {
+            const uint64_t block = ((uint64_t)(uintptr_t)buf >> 21) + 1;
+            const uint64_t e = atomic_load_explicit(&reader->ptr_cache[block & 7], memory_order_relaxed);
+            if ((e >> 1) == block && !(e & 1)) { /* known host memory */
+                const int64_t fi = st_lookup(reader, offset);
+                if (fi < 0)
+                    fast = 0;
+                else if ((uint64_t)fi >= reader->mir_lo && (uint64_t)fi < reader->mir_hi) {
+                    const size_t in_frame = offset - (size_t)reader->d_off[fi];
+                    const size_t n = MIN(count, (size_t)(reader->d_off[fi + 1] - reader->d_off[fi]) - in_frame);
+                    memcpy(buf, reader->h_mir[0] + (offset - reader->d_off[reader->mir_lo]), n);
+                    fast = (ssize_t)n;
+                }
+            }
+        }
+        pthread_rwlock_unlock(&reader->res_lock);
+        if (fast != -2)
+            return fast;
     }
     pthread_mutex_lock(&reader->lock);
     ssize_t ret = pread_locked(reader, buf, count, offset, call_data, errbuf);

@@ -490,6 +490,13 @@ int zsk_cuda_stream_sync(zsk_cuda_ctx *cx, int stream)
     return 0;
 }
 
+/* spinning wait: for copies of a few KiB, where the ~30 us wake-up of a blocking wait would be most of the call */
+int zsk_cuda_stream_sync_spin(zsk_cuda_ctx *cx, int stream)
+{
+    CK(cx, cudaStreamSynchronize(cx->streams[stream]));
+    return 0;
+}
+
 int zsk_cuda_stream_wait(zsk_cuda_ctx *cx, int waiter, int signaler)
 {
     CK(cx, cudaSetDevice(cx->device));

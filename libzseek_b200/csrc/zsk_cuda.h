@@ -39,7 +39,8 @@ int zsk_cuda_malloc_host(zsk_cuda_ctx *cx, void **p, size_t n);   /* pinned */
 int zsk_cuda_free_host(zsk_cuda_ctx *cx, void *p);
 int zsk_cuda_memset_async(zsk_cuda_ctx *cx, void *p, int v, size_t n, int stream);
 int zsk_cuda_memcpy_async(zsk_cuda_ctx *cx, void *dst, const void *src, size_t n, int kind, int stream);
-int zsk_cuda_stream_sync(zsk_cuda_ctx *cx, int stream);
+int zsk_cuda_stream_sync(zsk_cuda_ctx *cx, int stream);       /* the caller sleeps (blocking event) */
+int zsk_cuda_stream_sync_spin(zsk_cuda_ctx *cx, int stream);  /* the caller spins: lowest latency, for tiny copies */
 /* ZSK_STREAM_USER: a caller-owned cudaStream_t (NULL = the legacy default stream) that stream-ordered calls enqueue on */
 void zsk_cuda_set_user_stream(zsk_cuda_ctx *cx, void *stream);
 int zsk_cuda_stream_wait(zsk_cuda_ctx *cx, int waiter, int signaler); /* waiter waits for work queued on signaler so far */

@@ -704,3 +704,78 @@ def test_eight_concurrent_callers_on_one_reader(lib, golden, name, torch_cuda):
         for r in own:
             r.close()
     assert not errors, errors[:3]
+
+
+# --------------------------------------------------------------------------- residency of random host readers, parked readers
+@pytest.mark.parametrize("mode", ["pinned", "hbm"])
+@pytest.mark.parametrize("name", ["zsyn_zstd3_128k", "zsyn_lz4_64k"])
+def test_random_host_readers_go_resident(lib, golden, name, mode, monkeypatch, torch_cuda):
+    """A host reader that keeps missing at random places gets its whole shard decoded once: into a pinned window (reads are
+    memcpys, taken without the reader mutex by the threads that share the reader) or — when the process-wide pinned budget
+    is spent, forced here with ZSEEK_B200_RESIDENT_MB=0 — into HBM (reads are small device-to-host copies).  Every byte must
+    still be the reference's (B1-B3: short reads at frame ends, 0 at EOF), from several threads at once."""
+    import threading
+    cases, _ = golden
+    c = cases[name]
+    monkeypatch.setenv("ZSEEK_B200_RESIDENT_AFTER", "4")
+    if mode == "hbm":
+        monkeypatch.setenv("ZSEEK_B200_RESIDENT_MB", "0")
+    with OraclePort(c["image"]) as op:
+        want = op.decode_all().tobytes()
+        frame_ends = [int(x) for x in op.d_off[1:]]
+    total = len(want)
+
+    def expect(off, cnt):
+        if off >= total:
+            return b""
+        return want[off:min(off + cnt, next(e for e in frame_ends if e > off))]
+
+    errors = []
+
+    def rand(rd, seed, n):
+        try:
+            rng = np.random.Generator(np.random.PCG64(seed))
+            for _ in range(n):
+                off, cnt = int(rng.integers(0, total + 50)), int(rng.choice([1, 100, 4096, 70000, 200000]))
+                r, b = rd.pread(cnt, off)
+                assert b == expect(off, cnt) and r == len(b), (mode, off, cnt)
+        except Exception as e:  # noqa: BLE001
+            errors.append(e)
+
+    with lib.Reader(image=c["image"], cache_size=0) as rd:
+        rand(rd, 1, 40)                     # isolated misses, then the residency switch
+        ts = [threading.Thread(target=rand, args=(rd, 10 + k, 200)) for k in range(6)]
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join()
+        assert not errors, errors[:3]
+        dev = torch_cuda.empty(5000, dtype=torch_cuda.uint8, device="cuda")      # a device destination still works
+        assert rd.pread_into(dev, 5000, 12345) == len(expect(12345, 5000))
+        assert dev[:len(expect(12345, 5000))].cpu().numpy().tobytes() == expect(12345, 5000)
+        rd.cache_clear()                    # leaves residency; the ordinary path serves again
+        rand(rd, 99, 10)
+    assert not errors, errors[:3]
+
+
+def test_parked_reader_state_is_reused_across_files(lib, golden, torch_cuda):
+    """zseek_reader_close parks the device side of a reader and the next open takes it over — whatever the next file looks like
+    (other codec, other frame size, more frames).  Open/close in a loop over all golden files, twice, checking sampled reads
+    and a whole-file decode every time."""
+    cases, _ = golden
+    names = sorted(cases)
+    for rnd in range(2):
+        for name in names if rnd == 0 else reversed(names):
+            c = cases[name]
+            with OraclePort(c["image"]) as op:
+                want = op.decode_all()
+            with lib.Reader(image=c["image"], cache_size=rnd) as rd:
+                assert rd.size == want.size
+                if want.size == 0:
+                    continue
+                for off in (0, want.size // 3, max(want.size - 100, 0)):
+                    r, b = rd.pread(5000, off)
+                    assert r > 0 and b == want[off:off + r].tobytes(), (name, off)
+                dev = torch_cuda.empty(rd.size, dtype=torch_cuda.uint8, device="cuda")
+                assert rd.decode_frames(0, rd.frames, dev) == rd.size
+                assert (dev.cpu().numpy() == want).all(), name
