@@ -312,8 +312,13 @@ __global__ void __launch_bounds__(ZSK_LZ4L_THREADS) zsk_lz4_decode_lane_kernel(z
                 /* flushed long ago: [p - 15, p + 31) lies below opp - NEAR + 31, and fewer than 56 + 24*DEPTH + 8 bytes are unflushed */
                 const uint8_t *p = out + (opp - muse);
                 const uint32_t b = (uint32_t)((uintptr_t)p & 15u);
+#ifdef ZSK_EXP_L_NOFAR /* ablation build: what do the far match-source loads cost? (the decoded bytes are then wrong) */
+                if (mlen == 77u)
+#endif
+                {
                 zsk_cp16(stg + (slot * 2u) * 128u, p - b);
                 if (b + mlen > 16u) zsk_cp16(stg + (slot * 2u + 1u) * 128u, p - b + 16);
+                }
                 nm = nlit | (mlen << 4) | ZSK_L_MOP_FAR | (b << 16);
             }
             opp += mlen;
@@ -367,6 +372,9 @@ __global__ void __launch_bounds__(ZSK_LZ4L_THREADS) zsk_lz4_decode_lane_kernel(z
                         /* ONE 256-bit store per sector: an SM retires scattered sector writes slowly (~5 cycles each, measured
                          * on the zstd FSE stage), and 32 lanes write 32 different sectors here */
                         const uint32_t v[8] = { fp[0], fp[32], fp[64], fp[96], fp[128], fp[160], fp[192], fp[224] };
+#ifdef ZSK_EXP_L_NOFLUSH /* ablation build (tools/variant_sweep.py): what do the output stores cost? */
+                        if (v[0] == 0x12345678u && v[7] == 0x9abcdef0u)
+#endif
                         zsk_st256((uint32_t *)(out + flushed), v);
 #endif
                         flushed += 32u;
