@@ -17,6 +17,7 @@
 #define ZSK_LDG(p) (*(p))
 #define ZSK_STCG(p, v) (*(p) = (v))
 #define ZSK_PREFETCH_L1(p) ((void)(p))
+#define ZSK_PREFETCH_L2(p) ((void)(p))
 #else
 #include <cuda_runtime.h>
 #define ZSK_LDG(p) __ldg(p)
@@ -24,6 +25,7 @@
  * read streams of the same SM live in) */
 #define ZSK_STCG(p, v) __stcg((p), (v))
 #define ZSK_PREFETCH_L1(p) asm volatile("prefetch.global.L1 [%0];" ::"l"(p))
+#define ZSK_PREFETCH_L2(p) asm volatile("prefetch.global.L2 [%0];" ::"l"(p))
 #endif
 
 #define ZSK_FULL 0xffffffffu

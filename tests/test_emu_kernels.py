@@ -56,7 +56,7 @@ def test_emulated_zstd_bitstream_ring_across_a_4gib_address_boundary(emu, golden
     c = cases[name]
     with OraclePort(c["image"]) as op:
         payload = int(op.c_off[-1])
-        for wrap_at in list(range(16, payload, max(16, payload // 23))) + [payload - 7]:
+        for wrap_at in list(range(16, payload, max(16, payload // 9))) + [payload - 7]:   # ~10 full decodes per file keep the CPU suite short
             out, status = emu_api.decode_all(emu, c["image"], op.codec, op.c_off, op.d_off, ctas=2, wrap_at=wrap_at)
             assert (status == 0).all(), (wrap_at, status)
             assert hashlib.sha256(out.tobytes()).hexdigest() == c["input_sha256"], wrap_at
