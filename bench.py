@@ -227,6 +227,12 @@ def cpu_scan_stats(image, sample, threads, runs=5):
     return sample / ts[len(ts) // 2] / GB, sample / ts[0] / GB
 
 
+def step_stats(ms):
+    """best / median / worst of the per-step device times of one leg (rank 0)."""
+    s = sorted(ms)
+    return {"best": round(s[0], 3), "median": round(s[len(s) // 2], 3), "worst": round(s[-1], 3), "n": len(s)}
+
+
 def gen_offsets(n, total, count, seed=1):
     rng = np.random.Generator(np.random.PCG64(seed))
     return rng.integers(0, total - count, n, dtype=np.uint64)
@@ -308,16 +314,17 @@ def run_b200(args, rank, world):
         if sampler:
             sampler.mark_start()
         rd.timer_start()
-        kernel_ms = 0.0
+        kernel_ms, step_ms = 0.0, []
         for _ in range(steps):
             rd.decode_frames(0, rd.frames, dev_out)                           # inputs (C + D per step) >> L2: no flush needed
             kernel_ms += rd.last_decode_ms
+            step_ms.append(float(rd.last_decode_ms))                          # CUDA events around this step's launches
         dev_ms = rd.timer_stop()
         barrier()
         if sampler:
             sampler.mark_end()
         res = dict(total=total, C=C, frames=rd.frames, dev_ms=max_over_ranks(dev_ms), kernel_ms=max_over_ranks(kernel_ms),
-                   launches=rd.launch_count - l0, kernel=rd.last_decode_kernel,
+                   launches=rd.launch_count - l0, kernel=rd.last_decode_kernel, step_ms=step_ms,
                    verified=int(min_over_ranks(verify_device(dev_out, total, period))))
         return res, rd, pinned, dev_out
 
@@ -564,6 +571,7 @@ def run_b200(args, rank, world):
         def roof(r, steps=args.steps):
             ach = (r["C"] + r["total"]) * steps / (r["kernel_ms"] / 1e3) / GB
             return {"bound": "hbm", "achieved": round(ach, 1), "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 4),
+                    "frac_of_nominal_8000": round(ach / 8000.0, 4),
                     "traffic": profile_traffic(r["kernel"]), "kernel": r["kernel"], "algorithmic_bytes_per_launch": r["C"] + r["total"]}
 
         config = workload_config(args)
@@ -579,6 +587,8 @@ def run_b200(args, rank, world):
                            "cpu_baseline": ({"value": cpu["zstd3"]["gbps"], "best": cpu["zstd3"]["best"], "unit": "GB/s", "cores": cpu["zstd3"]["threads"],
                                              "kind": "reference", "one_thread": cpu["zstd3"]["gbps_1t"]} if cpu else None)},
             "kernel_ms_lz4_sum": round(lz["kernel_ms"], 3),
+            # SURVEY §8d "best and median of >= 5": per-step kernel times of this rank (events around each step's launches)
+            "step_ms_lz4": step_stats(lz["step_ms"]), "step_ms_zstd3": step_stats(zs["step_ms"]),
         }
         if dropin is not None:
             extra["dropin_plain_zseek_pread"] = dropin

@@ -17,7 +17,8 @@
  *
  * Environment (read at open): ZSEEK_B200_DEVICE (ordinal; default LOCAL_RANK, else current device),
  * ZSEEK_B200_READAHEAD (max frames decoded ahead of a sequential scan; 0 disables),
- * ZSEEK_B200_STAGE_MB (pinned ingest staging, default 64).
+ * ZSEEK_B200_STAGE_MB (pinned ingest staging, default 64).  INTEGRATION.md lists every knob (read-ahead ramp,
+ * residency of random host readers, parked readers, pinned-memory budgets, pread(2) worker threads).
  */
 #ifndef ZSEEK_B200_H
 #define ZSEEK_B200_H
