@@ -227,6 +227,24 @@ def cpu_scan_stats(image, sample, threads, runs=5):
     return sample / ts[len(ts) // 2] / GB, sample / ts[0] / GB
 
 
+def cpu_leg(corpus, fname):
+    """The reference on all host cores (and on one) over the first GiB of one corpus file: warm-up, median and best of 5."""
+    image = corpus.image(fname, 1)
+    threads = os.cpu_count() or 1
+    sample = min(corpus.tile, 1 << 30)
+    med, best = cpu_scan_stats(image, sample, threads)
+    med1, _ = cpu_scan_stats(image, min(sample, 256 * MIB), 1, runs=3)
+    return dict(gbps=round(med, 3), best=round(best, 3), gbps_1t=round(med1, 3), threads=threads, sample=sample)
+
+
+def cpu_leg_subprocess(args, fname):
+    cmd = [sys.executable, os.path.abspath(__file__), "--cpu-leg", fname, "--size-gib", str(args.size_gib), "--tile-mib", str(args.tile_mib)]
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    if p.returncode != 0:
+        raise RuntimeError(p.stderr[-300:])
+    return json.loads(p.stdout.strip().splitlines()[-1])
+
+
 def step_stats(ms):
     """best / median / worst of the per-step device times of one leg (rank 0)."""
     s = sorted(ms)
@@ -545,14 +563,19 @@ def run_b200(args, rank, world):
     # ---------------- CPU baseline (the reference build) on rank 0, N = 1 only (other ranks would share the host cores)
     cpu = {}
     if rank == 0 and world == 1:
-        threads = os.cpu_count() or 1
+        # The multi-thread figure of these VMs is bimodal between invocations seconds apart (LZ4, 16 threads, same box:
+        # 37 / 45 / 53 GB/s; within one invocation median ~ best), whichever process runs it (profiles/README.md,
+        # r02_final*).  So the leg is timed twice — in a process of its own (the harness of --impl reference) and in
+        # this process — 5 passes each after a warm-up, and `value` is the BETTER median: the CPU gets its best showing.
         for name, fname in (("lz4", "lz4.zsk"), ("zstd3", "zstd3.zsk")):
-            image = corpus.image(fname, 1)
-            sample = min(corpus.tile, 1 << 30)
-            med, best = cpu_scan_stats(image, sample, threads)
-            med1, best1 = cpu_scan_stats(image, min(sample, 256 * MIB), 1, runs=3)
-            cpu[name] = dict(gbps=round(med, 3), best=round(best, 3), gbps_1t=round(med1, 3), threads=threads, sample=sample)
-            del image
+            legs = []
+            try:
+                legs.append(dict(cpu_leg_subprocess(args, fname), process="own process"))
+            except Exception as e:  # noqa: BLE001
+                log(f"[bench] CPU leg {name} in a subprocess failed ({e})")
+            legs.append(dict(cpu_leg(corpus, fname), process="bench process"))
+            cpu[name] = dict(max(legs, key=lambda c: c["gbps"]))
+            cpu[name]["all"] = [{"timed_in": c["process"], "median": c["gbps"], "best": c["best"]} for c in legs]
 
     dropin = None
     if rank == 0 and world == 1 and args.dropin_mib > 0:
@@ -585,7 +608,8 @@ def run_b200(args, rank, world):
                            "e2e": {"value": round(zs["total"] * world * args.steps / zs["e2e_s"] / GB, 2), "unit": "GB/s",
                                    "verified_bytes": zs["e2e_verified"], "h2d_bytes_per_step": zs["C"], "d2h_bytes_per_step": zs["total"]},
                            "cpu_baseline": ({"value": cpu["zstd3"]["gbps"], "best": cpu["zstd3"]["best"], "unit": "GB/s", "cores": cpu["zstd3"]["threads"],
-                                             "kind": "reference", "one_thread": cpu["zstd3"]["gbps_1t"]} if cpu else None)},
+                                             "kind": "reference", "one_thread": cpu["zstd3"]["gbps_1t"], "timed_in": cpu["zstd3"]["process"],
+                                             "all_timings": cpu["zstd3"]["all"]} if cpu else None)},
             "kernel_ms_lz4_sum": round(lz["kernel_ms"], 3),
             # SURVEY §8d "best and median of >= 5": per-step kernel times of this rank (events around each step's launches)
             "step_ms_lz4": step_stats(lz["step_ms"]), "step_ms_zstd3": step_stats(zs["step_ms"]),
@@ -643,7 +667,9 @@ def run_b200(args, rank, world):
             "roofline": dict(roof(lz), peak_source=peak_src),
             "cpu_baseline": ({"value": cpu["lz4"]["gbps"], "best": cpu["lz4"]["best"], "unit": "GB/s", "cores": cpu["lz4"]["threads"], "kind": "reference",
                               "sample": (f"first {cpu['lz4']['sample'] >> 20} MiB of the same file, one reader per thread, 1 MiB zseek_pread requests, "
-                                         f"cache_size 0, warm-up + 5 passes: value = median, best alongside; 1 thread: {cpu['lz4']['gbps_1t']} GB/s")}
+                                         f"cache_size 0, warm-up + 5 passes, timed twice (own process / bench process): value = the better median "
+                                         f"({cpu['lz4']['process']}), best alongside; 1 thread: {cpu['lz4']['gbps_1t']} GB/s"),
+                              "all_timings": cpu["lz4"]["all"]}
                              if cpu else {"value": None, "unit": "GB/s", "cores": 0, "kind": "reference",
                                           "sample": "timed at N = 1 only; see the --impl reference line of this N"}),
             "extra": extra,
@@ -735,12 +761,16 @@ def main():
     ap.add_argument("--random-gib", type=float, default=16.0, help="size of the zstd-3 file of the random-read leg (configs[3]: 16)")
     ap.add_argument("--c5-gib", type=float, default=8.0, help="per-GPU size of the configs[4] legs (0 = skip)")
     ap.add_argument("--dropin-mib", type=int, default=1024, help="file size of the plain-zseek_pread drop-in leg at N = 1 (0 = skip)")
+    ap.add_argument("--cpu-leg", default="", help="internal: time the reference on the host cores over this corpus file and print one JSON object")
     args = ap.parse_args()
     if args.tile_mib <= 0:
         args.tile_mib = int(args.size_gib * 1024)
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     claim_stdout()
+    if args.cpu_leg:
+        emit(cpu_leg(Corpus(args), args.cpu_leg))
+        return
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
