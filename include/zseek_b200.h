@@ -79,7 +79,9 @@ ZSEEK_EXPORT ssize_t zseek_b200_pread_batch(zseek_reader_t *reader, size_t n, co
  * batch slab of the reader, not into the LRU cache.  Results are defined exactly like zseek_b200_pread_batch.
  * zseek_b200_batch_wait waits for the most recent async batch and returns 0, or -1 with the first frame error
  * ("decompress frame: ...", "frame outside this reader's shard"); dev_dst of requests in failed frames is undefined.
- * One async batch per reader may be in flight (the next call waits for the previous one). */
+ * One async batch per reader may be in flight (the next call waits for the previous one).  Every other entry point of
+ * the reader may be called while a batch is pending: its device work is ordered after the batch (an event wait on the
+ * reader's streams, the host does not block).  The caller's stream must stay alive until zseek_b200_batch_wait. */
 ZSEEK_EXPORT ssize_t zseek_b200_pread_batch_async(zseek_reader_t *reader, size_t n, const uint64_t *dev_offsets,
                                                   const uint64_t *dev_counts, uint64_t fixed_count, void *dev_dst,
                                                   const uint64_t *dev_dst_offs, uint64_t dst_stride, int64_t *dev_results,

@@ -196,6 +196,18 @@ static uint8_t *mirror_half(zseek_reader_t *r, int which);
 static size_t env_size(const char *name, size_t dflt);
 static bool stream_frames_to_host(zseek_reader_t *r, uint64_t lo, uint64_t hi, uint8_t *dst, void *call_data, char *errbuf);
 
+/* A stream-ordered batch queued on a CALLER stream is invisible to the reader's own streams.  Before any other entry point
+ * touches what that batch uses (compressed image, batch scratch, the context's zstd scratch pools), the reader's streams
+ * are made to wait for it on the device; the host does not block and the batch's verdict stays pending for
+ * zseek_b200_batch_wait. */
+static void async_fence(zseek_reader_t *r)
+{
+    if (r->async_stream != ZSK_STREAM_USER)
+        return;
+    zsk_cuda_stream_wait(r->cx, ZSK_STREAM_COMPUTE, ZSK_STREAM_USER);
+    zsk_cuda_stream_wait(r->cx, ZSK_STREAM_H2D, ZSK_STREAM_USER);
+}
+
 static void set_error(char errbuf[ZSEEK_ERRBUF_SIZE], const char *fmt, ...)
 {
     if (!errbuf)
@@ -1312,6 +1324,7 @@ static ssize_t pread_locked(zseek_reader_t *r, void *buf, size_t count, size_t o
         return 0; /* B3 */
     if (!in_shard(r, f, errbuf))
         return -1;
+    async_fence(r);
     int on_device = buf_on_device(r, buf);
     if (!on_device && f >= r->mir_lo && f < r->mir_hi) { /* pinned window hit: plain memcpy */
         memcpy(buf, mirror_half(r, r->mir_cur) + (offset - r->d_off[r->mir_lo]), n);
@@ -1506,6 +1519,7 @@ bool zseek_b200_set_shard(zseek_reader_t *r, unsigned rank, unsigned world, char
         return false;
     }
     pthread_mutex_lock(&r->lock);
+    async_fence(r);
     prefetch_drop(r);
     drop_resident(r);
     r->shard_lo = r->nframes * rank / world;
@@ -1541,6 +1555,7 @@ bool zseek_b200_load(zseek_reader_t *r, size_t lo, size_t hi, void *call_data, c
         return false;
     }
     pthread_mutex_lock(&r->lock);
+    async_fence(r);
     prefetch_drop(r);
     bool ok = ensure_resident(r, lo, hi, call_data, errbuf) && (zsk_cuda_stream_sync(r->cx, ZSK_STREAM_H2D) == 0);
     pthread_mutex_unlock(&r->lock);
@@ -1603,6 +1618,7 @@ ssize_t zseek_b200_decode_frames(zseek_reader_t *r, size_t lo, size_t hi, void *
         return -1;
     }
     pthread_mutex_lock(&r->lock);
+    async_fence(r);
     prefetch_drop(r);
     ssize_t ret = -1;
     if (lo == hi)
@@ -1899,6 +1915,7 @@ ssize_t zseek_b200_read_range(zseek_reader_t *r, void *buf, size_t count, size_t
         return -1;
     }
     pthread_mutex_lock(&r->lock);
+    async_fence(r);
     prefetch_drop(r);
     ssize_t ret = -1;
     size_t total = (size_t)r->d_off[r->nframes];
@@ -1971,6 +1988,7 @@ ssize_t zseek_b200_pread_batch(zseek_reader_t *r, size_t n, const uint64_t *offs
         return -1;
     }
     pthread_mutex_lock(&r->lock);
+    async_fence(r);
     prefetch_drop(r);
     ssize_t ret = -1;
     uint64_t N = r->nframes;
@@ -2194,8 +2212,15 @@ ssize_t zseek_b200_pread_batch_async(zseek_reader_t *r, size_t n, const uint64_t
         r->bs_cap = cap;
     }
     const int sidx = stream ? ZSK_STREAM_USER : ZSK_STREAM_COMPUTE;
-    if (stream)
+    if (stream) {
         zsk_cuda_set_user_stream(r->cx, stream);
+        /* the caller's stream has never seen what the reader's own streams did (image upload, earlier launches that
+         * use the same scratch): order it after them */
+        if (zsk_cuda_stream_wait(r->cx, ZSK_STREAM_USER, ZSK_STREAM_H2D) || zsk_cuda_stream_wait(r->cx, ZSK_STREAM_USER, ZSK_STREAM_COMPUTE)) {
+            cuda_fail(r, errbuf, "order streams");
+            goto out;
+        }
+    }
     zsk_lookup_args la = { r->g_doff, (uint32_t)N, dev_offsets, dev_counts, fixed_count, (uint32_t)n,
                            r->g_b_frame, r->g_b_inframe, r->g_b_nbytes, r->g_touched };
     zsk_compact_args ca = { r->g_touched, (uint32_t)N, (uint32_t)r->shard_lo, (uint32_t)r->shard_hi, r->slot_size, r->bs_cap,
@@ -2233,6 +2258,7 @@ void zseek_b200_cache_clear(zseek_reader_t *r)
     if (!r)
         return;
     pthread_mutex_lock(&r->lock);
+    async_fence(r);
     prefetch_drop(r);
     drop_resident(r);
     cache_clear(r);
@@ -2244,6 +2270,7 @@ void zseek_b200_unload(zseek_reader_t *r)
     if (!r)
         return;
     pthread_mutex_lock(&r->lock);
+    async_fence(r);
     prefetch_drop(r);
     zsk_cuda_stream_sync(r->cx, ZSK_STREAM_COMPUTE);
     r->res_lo = r->res_hi = 0;

@@ -648,6 +648,62 @@ def test_async_batch_on_a_caller_stream_matches_a_loop_of_reference_preads(lib, 
         assert dst[:4096].cpu().numpy().tobytes() == data[100:4196]          # the good frames of the batch are served
 
 
+@pytest.mark.skipif(not have_reference(), reason="oracle/_ref/libzseek_ref.so missing")
+@pytest.mark.parametrize("codec,level,frame", [(LZ4, 0, 65536), (ZSTD, 3, 262144)])
+def test_other_calls_while_an_async_batch_is_pending_on_a_caller_stream(lib, codec, level, frame, torch_cuda):
+    """A stream-ordered batch queued on a CALLER stream shares the compressed image, the batch scratch and the zstd scratch
+    pools with every other entry point of the reader.  Calls made before zseek_b200_batch_wait must order themselves after
+    it on the device (async_fence) instead of racing it: both the pending batch and the interleaved calls return the
+    right bytes."""
+    torch = torch_cuda
+    from datagen import refwriter, zsyn
+    data = zsyn.gen(6 << 20, seed=77)
+    ref = np.frombuffer(data, dtype=np.uint8)
+    image = refwriter.write(data, codec, level, frame)
+    total = len(data)
+    rng = np.random.Generator(np.random.PCG64(5))
+    stream = torch.cuda.Stream()
+    with lib.Reader(image=image, cache_size=4) as rd:
+        rd.load(0, rd.frames)
+        for rnd in range(4):
+            n = 2000
+            offs = rng.integers(0, total - 4096, n).astype(np.uint64)
+            d_offs = torch.from_numpy(offs.astype(np.int64)).cuda()
+            d_res = torch.full((n,), -7, dtype=torch.int64, device="cuda")
+            dst = torch.full((n * 4096,), 0x5A, dtype=torch.uint8, device="cuda")
+            whole = torch.zeros(rd.size + 64, dtype=torch.uint8, device="cuda")
+            busy = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
+            o2 = rng.integers(0, total - 4096, 500).astype(np.uint64)
+            out2 = np.zeros(500 * 4096, dtype=np.uint8)
+            torch.cuda.synchronize()                      # the tensors above exist before any other stream touches them
+            # a few ms of fills on the caller stream first, so that the batch is certainly still pending below
+            with torch.cuda.stream(stream):
+                for _ in range(24):
+                    busy.fill_(rnd)
+                rd.pread_batch_async(d_offs, dst, fixed_count=4096, dst_stride=4096, dev_results=d_res, stream=stream)
+            # no wait: other entry points of the same reader
+            res2 = rd.pread_batch(o2, fixed_count=4096, dst=out2, dst_stride=4096)
+            assert rd.decode_frames(0, rd.frames, whole) == rd.size
+            r3, b3 = rd.pread(3000, int(offs[0]) // 2)
+            rd.batch_wait()
+            stream.synchronize()
+            d_off = np.asarray(rd.d_off, dtype=np.uint64)
+
+            def expect(o):
+                end = int(d_off[np.searchsorted(d_off, o, side="right")])
+                return min(4096, end - int(o))
+            res, out = d_res.cpu().numpy(), dst.cpu().numpy()
+            for i in range(n):
+                k = expect(offs[i])
+                assert res[i] == k, (rnd, i)
+                assert (out[i * 4096:i * 4096 + k] == ref[int(offs[i]):int(offs[i]) + k]).all(), (rnd, i)
+            for i in range(500):
+                k = expect(o2[i])
+                assert res2[i] == k and (out2[i * 4096:i * 4096 + k] == ref[int(o2[i]):int(o2[i]) + k]).all(), (rnd, i)
+            assert (whole[:rd.size].cpu().numpy() == ref).all(), rnd
+            assert b3 == data[int(offs[0]) // 2:int(offs[0]) // 2 + r3] and r3 > 0
+
+
 @pytest.mark.parametrize("name", ["mix_lz4", "zsyn_zstd3_128k"])
 def test_eight_concurrent_callers_on_one_reader(lib, golden, name, torch_cuda):
     """zseek_pread and zseek_reader_stats may be called concurrently on one reader.  Eight threads
