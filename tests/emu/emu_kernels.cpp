@@ -72,6 +72,50 @@ void emu_decode(int codec, const uint8_t *comp, uint64_t comp_base, const uint64
     else emu_zstd_pipeline(a, njobs, ctas, d_off, first_frame, frame_ids, codec == 201);
 }
 
+/* The device side of a stream-ordered batch (reader.c zseek_b200_pread_batch_async), kernel after kernel as the product
+ * queues them: K1 lookup -> zsk_compact_kernel (touched frames -> job list, frame -> slot map, job COUNT in "device"
+ * memory) -> decode launch that reads the job count through njobs_dev (njobs = upper bound) with per-job limits ->
+ * K4 gather that also writes the results.  ctl[0] = job count, ctl[1] = error flag of the compaction. */
+__attribute__((visibility("default")))
+void emu_batch(int codec, const uint8_t *comp, const uint64_t *c_off, const uint64_t *d_off, uint32_t nframes,
+               uint32_t shard_lo, uint32_t shard_hi, const uint64_t *offsets, const uint64_t *counts, uint64_t fixed_count,
+               uint32_t n, uint64_t slot_size, uint32_t max_jobs, uint8_t *slab, uint8_t *dst, uint64_t dst_stride,
+               int64_t *results, int32_t *job_status, uint32_t *ctl, int use_limits, uint32_t ctas)
+{
+    std::vector<int32_t> frame(n + 1);
+    std::vector<uint32_t> inframe(n + 1), nbytes(n + 1), touched(nframes + 1, 0u);
+    std::vector<uint32_t> job_ids(max_jobs + 1, 0xEEEEEEEEu), job_limits(max_jobs + 1, 0xEEEEEEEEu);
+    std::vector<uint64_t> job_offs(max_jobs + 1, ~0ull);
+    std::vector<int64_t> frame_src(nframes + 1, -7);
+    ctl[0] = ctl[1] = 0;
+    zsk_lookup_args la{d_off, nframes, offsets, counts, fixed_count, n, frame.data(), inframe.data(), nbytes.data(), touched.data()};
+    emu::launch(dim3(2), dim3(256), 0, [&] { zsk_lookup_kernel(la); });
+    zsk_compact_args ca{touched.data(), nframes, shard_lo, shard_hi, slot_size, max_jobs, job_ids.data(), job_offs.data(),
+                        job_limits.data(), frame_src.data(), ctl, ctl + 1};
+    emu::launch(dim3(2), dim3(256), 0, [&] { zsk_compact_kernel(ca); });
+    if (max_jobs) {
+        uint32_t counter = 0;
+        std::vector<uint8_t> scratch((size_t)ctas * ZSK_LIT_SCRATCH + 64);
+        zsk_decode_args a{};
+        a.c_off = c_off; a.d_off = d_off; a.comp = comp; a.comp_base = 0; a.frame_ids = job_ids.data();
+        a.dst_offs = job_offs.data(); a.dst = slab; a.dst_base = 0; a.first_frame = 0; a.njobs = max_jobs;
+        a.status = job_status; a.work_counter = &counter; a.scratch = scratch.data();
+        a.limits = use_limits ? job_limits.data() : nullptr;
+        a.njobs_dev = ctl; a.job_base = 0;
+        if (codec == 1) emu::launch(dim3(ctas), dim3(ZSK_LZ4_CTA_THREADS), 0, [&] { zsk_lz4_decode_batch_kernel(a); });
+        else if (codec == 102) emu::launch(dim3(ctas), dim3(ZSK_LZ4L_THREADS), ZSK_LZ4L_SMEM, [&] { zsk_lz4_decode_lane_kernel(a); });
+        else {
+            /* pools sized like the launch layer does it: from the upper bound of the job count */
+            std::vector<uint32_t> ids(max_jobs);
+            const uint32_t live = ctl[0] < max_jobs ? ctl[0] : max_jobs;
+            for (uint32_t j = 0; j < max_jobs; j++) ids[j] = j < live ? job_ids[j] : (live ? job_ids[0] : 0u);
+            emu_zstd_pipeline(a, max_jobs, ctas, d_off, 0, ids.data(), false);
+        }
+    }
+    zsk_gather_args ga{frame.data(), inframe.data(), nbytes.data(), frame_src.data(), slab, dst, nullptr, dst_stride, n, results};
+    emu::launch(dim3(2), dim3(256), 0, [&] { zsk_gather_kernel(ga); });
+}
+
 __attribute__((visibility("default")))
 void emu_lookup(const uint64_t *d_off, uint32_t nframes, const uint64_t *offsets, const uint64_t *counts,
                 uint64_t fixed_count, uint32_t n, int32_t *frame, uint32_t *inframe, uint32_t *nbytes, uint32_t *touched)

@@ -56,7 +56,7 @@ def test_emulated_zstd_bitstream_ring_across_a_4gib_address_boundary(emu, golden
     c = cases[name]
     with OraclePort(c["image"]) as op:
         payload = int(op.c_off[-1])
-        for wrap_at in list(range(16, payload, max(16, payload // 9))) + [payload - 7]:   # ~10 full decodes per file keep the CPU suite short
+        for wrap_at in list(range(16, payload, max(16, payload // 6))) + [payload - 7]:   # ~7 full decodes per file keep the CPU suite short
             out, status = emu_api.decode_all(emu, c["image"], op.codec, op.c_off, op.d_off, ctas=2, wrap_at=wrap_at)
             assert (status == 0).all(), (wrap_at, status)
             assert hashlib.sha256(out.tobytes()).hexdigest() == c["input_sha256"], wrap_at
@@ -158,6 +158,41 @@ def test_emulated_lookup_and_gather(emu, golden):
         for i in range(n):
             o, k = int(offsets[i]), int(nbytes[i])
             assert (dst[i * stride:i * stride + k] == decoded[o:o + k]).all()
+
+
+@pytest.mark.parametrize("name,codec,limits", [("zsyn_lz4_64k", 1, True), ("mix_lz4", 102, True), ("zsyn_lz4_256k_linked", 102, False),
+                                               ("zsyn_zstd3_128k", None, True), ("mix_zstd19", None, True), ("zsyn_zstd3_mt", None, False)])
+def test_emulated_stream_ordered_batch_chain(emu, golden, name, codec, limits):
+    """n1 on the CPU: the kernels of zseek_b200_pread_batch_async in the order the product queues them — lookup, compaction
+    of the touched frames into a job list whose COUNT stays in device memory, a decode launch that reads that count
+    (njobs is only an upper bound) and stops every frame at the last byte the batch needs of it, gather + results.
+    Every request must come out as the oracle's zseek_pread returns it; nothing outside the requested bytes is written."""
+    cases, _ = golden
+    c = cases[name]
+    with OraclePort(c["image"]) as op:
+        rng = np.random.Generator(np.random.PCG64(11))
+        d_off = np.asarray(op.d_off, dtype=np.int64)
+        offsets = np.concatenate([rng.integers(0, op.size + 50, 220), d_off[1:] - rng.integers(1, 300, op.frames), [op.size, op.size + 10 ** 9]]).astype(np.uint64)
+        counts = rng.choice([0, 1, 100, 4096], offsets.size).astype(np.uint64)
+        stride = 4096
+        dst, res, status, njobs, err = emu_api.batch(emu, c["image"], codec if codec is not None else op.codec, op.c_off, op.d_off,
+                                                     offsets, counts, stride, limits=limits)
+        assert err == 0
+        touched = {op.offset_to_frame(int(o)) for o, k in zip(offsets, counts) if op.pread(int(k), int(o))[0] > 0 or op.offset_to_frame(int(o)) >= 0}
+        touched.discard(-1)
+        assert njobs == len(touched)
+        assert (status[:njobs] == 0).all(), status[:njobs]
+        for i in range(offsets.size):
+            r, b = op.pread(int(counts[i]), int(offsets[i]))
+            assert res[i] == r, i
+            assert dst[i * stride:i * stride + r].tobytes() == b, i
+            assert (dst[i * stride + r:(i + 1) * stride] == 0x5A).all(), i
+        # a request outside the shard and a slab that is too small are flagged by the compaction, not silently dropped
+        assert emu_api.batch(emu, c["image"], codec if codec is not None else op.codec, op.c_off, op.d_off, offsets, counts, stride,
+                             shard=(0, max(1, op.frames // 2)), max_jobs=0)[4] == (1 if op.frames > 1 else 0)
+        if len(touched) > 1:
+            assert emu_api.batch(emu, c["image"], codec if codec is not None else op.codec, op.c_off, op.d_off, offsets, counts, stride,
+                                 max_jobs=1)[4] == 2
 
 
 def _shapes_corpus():
