@@ -47,7 +47,8 @@ struct zsk_cuda_ctx {
     const char *k_name;                  /* name of the most recent decode kernel */
     uint32_t *counters;                  /* ZSK_NCOUNTERS work counters, used round-robin */
     unsigned counter_next;
-    uint8_t *scratch;                    /* literal scratch of the one-CTA-per-frame zstd kernel (deferred frames only), zstd_ctas CTAs; lazily allocated */
+    uint8_t *scratch;                    /* literal scratch of the one-CTA-per-frame zstd kernel, ZSK_LIT_SCRATCH bytes for each of scratch_ctas CTAs; lazily allocated */
+    size_t scratch_ctas;
     int zstd_ctas, lz4_ctas;
     /* zstd pipeline (zsk_zstd_pipe.cuh): scratch pools grown on demand, per-launch counter blocks used round-robin */
     zsk_zframe *zframes;
@@ -211,7 +212,7 @@ size_t zsk_cuda_ctx_held(const zsk_cuda_ctx *cx)
 {
     return cx->zblocks_cap * sizeof(zsk_zblock) + cx->zseqs_cap * 3 * sizeof(uint32_t) + cx->zlits_cap +
            cx->zjobs_cap * (sizeof(zsk_zframe) + sizeof(uint32_t)) + cx->zbprog_cap * 2 * sizeof(uint32_t) +
-           (cx->scratch ? (size_t)cx->sm_count * ZSK_LIT_SCRATCH : 0);
+           cx->scratch_ctas * ZSK_LIT_SCRATCH;
 }
 
 /* gives back the scratch pools of a context that is being parked when they hold more than max_bytes */
@@ -568,17 +569,31 @@ static int grow_pool(zsk_cuda_ctx *cx, void **p, size_t *cap_bytes, size_t need)
     return 0;
 }
 
+/* literal scratch of the one-CTA-per-frame zstd kernel for launches of up to `ctas` CTAs.  A context keeps what it has; it
+ * grows only when a parked context that ran the pipeline (one wave for deferred frames) is taken over by a reader opened with
+ * ZSEEK_B200_ZSTD_LEGACY=1, whose launches use more CTAs. */
+static int ensure_lit_scratch(zsk_cuda_ctx *cx, size_t ctas)
+{
+    if (cx->scratch && cx->scratch_ctas >= ctas) return 0;
+    if (cx->scratch) {
+        CK(cx, cudaDeviceSynchronize());
+        CK(cx, cudaFreeAsync(cx->scratch, cx->alloc_stream));
+        cx->scratch = NULL;
+        cx->scratch_ctas = 0;
+    }
+    CK(cx, cudaMallocAsync((void **)&cx->scratch, ctas * ZSK_LIT_SCRATCH + ZSK_PAD_BACK, cx->alloc_stream));
+    CK(cx, cudaStreamSynchronize(cx->alloc_stream));
+    cx->scratch_ctas = ctas;
+    return 0;
+}
+
 /* zstd: index -> FSE sequences + Huffman literals -> execution -> (deferred frames) one-CTA-per-frame kernel */
 static int launch_zstd_pipeline(zsk_cuda_ctx *cx, zsk_decode_args a, cudaStream_t s, int stream)
 {
     const size_t njobs = a.njobs;
     const uint64_t dsum = a.dsize_sum ? a.dsize_sum : (uint64_t)njobs << 20;
     int rc;
-    if (!cx->scratch) /* deferred frames are rare: one wave of the old kernel is plenty */
-    {
-        CK(cx, cudaMallocAsync((void **)&cx->scratch, (size_t)cx->sm_count * ZSK_LIT_SCRATCH + ZSK_PAD_BACK, cx->alloc_stream));
-        CK(cx, cudaStreamSynchronize(cx->alloc_stream));
-    }
+    if ((rc = ensure_lit_scratch(cx, (size_t)cx->sm_count))) return rc; /* deferred frames are rare: one wave of the old kernel is plenty */
     if (njobs > cx->zjobs_cap) {
         size_t cap_f = cx->zjobs_cap * sizeof(zsk_zframe), cap_d = cx->zjobs_cap * sizeof(uint32_t);
         if ((rc = grow_pool(cx, (void **)&cx->zframes, &cap_f, njobs * sizeof(zsk_zframe)))) return rc;
@@ -660,10 +675,7 @@ int zsk_cuda_launch_decode(zsk_cuda_ctx *cx, int codec, const zsk_decode_args *a
         zsk_lz4_decode_batch_kernel<<<ctas, ZSK_LZ4_CTA_THREADS, 0, s>>>(a);
         cx->k_name = "zsk_lz4_decode_batch_kernel";
     } else if (codec == ZSK_CODEC_ZSTD && cx->zstd_legacy) {
-        if (!cx->scratch) {
-            CK(cx, cudaMallocAsync((void **)&cx->scratch, (size_t)cx->zstd_ctas * ZSK_LIT_SCRATCH + ZSK_PAD_BACK, cx->alloc_stream));
-            CK(cx, cudaStreamSynchronize(cx->alloc_stream));
-        }
+        if (int rc = ensure_lit_scratch(cx, (size_t)cx->zstd_ctas)) return rc;
         a.scratch = cx->scratch;
         unsigned ctas = a.njobs < (unsigned)cx->zstd_ctas ? a.njobs : (unsigned)cx->zstd_ctas;
         zsk_zstd_decode_kernel<<<ctas, ZSK_ZSTD_CTA_THREADS, 0, s>>>(a);
