@@ -62,7 +62,7 @@ def test_emulated_zstd_bitstream_ring_across_a_4gib_address_boundary(emu, golden
             assert hashlib.sha256(out.tobytes()).hexdigest() == c["input_sha256"], wrap_at
 
 
-@pytest.mark.parametrize("misalign", [1, 7, 15, 17, 31])
+@pytest.mark.parametrize("misalign", [1, 15, 17])
 @pytest.mark.parametrize("name", ["zsyn_zstd3_128k", "mix_zstd19"])
 def test_emulated_zstd_pipeline_unaligned_output(emu, golden, name, misalign):
     """The executor's ring is flushed in 16-byte vectors aligned on the GLOBAL address; heads and tails go bytewise."""

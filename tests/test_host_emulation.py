@@ -1,0 +1,162 @@
+"""Host logic of the reader (libzseek_b200/csrc/reader.c) without a GPU.
+
+tests/emu/libzsk_hostemu.so = the UNMODIFIED reader.c linked against a stand-in launch layer (tests/emu/hostemu.cpp) that
+keeps "device" memory on the host and runs the product's kernel sources on the lock-step emulator.  TEST INFRASTRUCTURE
+ONLY — not a fallback, never named by the product (test_abi.py::test_product_never_touches_the_oracle).  The scenarios
+are the GPU parity tests themselves (tests/test_gpu_parity.py, the ones that only use host buffers), called here with the
+emulated library on the small golden files, plus cache / parking checks through "device" buffers of the stand-in.  What
+this adds to the kernel-level emulator tests: seek table, LRU cache, read-ahead windows and their failure handling, batch
+bookkeeping, callbacks and I/O errors — the reference components src/decompress.c, src/cache.c, src/buffer.c replaced by
+reader.c — are checked against the reference's golden vectors in the no-GPU container."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import emu_api
+import test_gpu_parity as G
+from oracle.pyapi import ZSTD, OraclePort, have_reference
+
+HOSTEMU = os.path.join(emu_api.EMU_DIR, "libzsk_hostemu.so")
+
+
+@pytest.fixture(scope="module")
+def hostlib():
+    """The libzseek_b200 Python mirror bound to the emulated library for the duration of this module."""
+    subprocess.run(["make", "-C", emu_api.EMU_DIR, "-s", "libzsk_hostemu.so"], check=True, stderr=subprocess.DEVNULL)
+    import libzseek_b200 as z
+    from libzseek_b200 import reader as R
+    saved = (R._lib, R.LIB_PATH)
+    R._lib, R.LIB_PATH = None, HOSTEMU
+    try:
+        L = z.load_library()
+        L.hostemu_device_alloc.restype = C.c_void_p
+        L.hostemu_device_alloc.argtypes = [C.c_size_t]
+        L.hostemu_device_free.argtypes = [C.c_void_p]
+        L.hostemu_device_allocs.restype = C.c_size_t
+        yield z
+    finally:
+        R._lib, R.LIB_PATH = saved
+
+
+GOLDEN_RUNS = [("tiny_zstd", 0), ("tiny_zstd", 1), ("tiny_lz4", 0), ("tiny_lz4", 4), ("zsyn_zstd3_128k", 0), ("zsyn_zstd3_128k", 4),
+               ("zsyn_zstd3_mt", 1), ("zsyn_zstd19_256k", 0)]
+
+
+@pytest.mark.parametrize("name,cache_size", GOLDEN_RUNS)
+def test_golden_preads_through_the_host_code(hostlib, golden, name, cache_size):
+    """every golden zseek_pread call (return value + bytes of the reference reader), stats, whole-file scan"""
+    G.test_pread_matches_reference_golden(hostlib, golden, name, cache_size, None)
+
+
+def test_read_cursor_callbacks_and_io_errors(hostlib, golden):
+    G.test_python_callbacks_reader(hostlib, golden, None)
+    G.test_io_errors_surface_like_the_reference(hostlib, golden, None)
+    # zseek_read: the cursor advances by what each call returned (reference src/decompress.c:826-835)
+    cases, _ = golden
+    c = cases["zsyn_zstd3_256k_chunks"]
+    with OraclePort(c["image"]) as op:
+        want = op.decode_all().tobytes()
+    with hostlib.Reader(image=c["image"], cache_size=2) as rd:
+        got = bytearray()
+        while True:
+            r, b = rd.read(70001)
+            if r == 0:
+                break
+            got += b
+    assert bytes(got) == want
+
+
+def test_scan_over_a_file_handle(hostlib, golden):
+    """reference test/example.c:36-87 over a FILE* (default I/O callbacks), 4 KiB preads, cache_size 1"""
+    G.test_example_scan_4k_cache1(hostlib, golden, "mix_zstd19", None)
+
+
+def test_host_batch_semantics(hostlib, golden):
+    """zseek_b200_pread_batch into host memory stores exactly what a loop of zseek_pread stores (sentinel bytes survive)"""
+    G.test_host_batch_leaves_unproduced_bytes_untouched(hostlib, golden, None)
+
+
+def test_corrupt_frames(hostlib, golden):
+    G.test_corrupt_frame_fails_instead_of_hanging(hostlib, golden, None)
+
+
+@pytest.mark.skipif(not have_reference(), reason="verdicts come from oracle/_ref")
+def test_read_ahead_window_with_a_bad_frame(hostlib, golden):
+    """a bad frame inside a read-ahead window fails only the reads of that frame (reference src/decompress.c:700-790)"""
+    G.test_sequential_scan_across_a_corrupt_frame(hostlib, golden, None)
+
+
+def test_shard_limits(hostlib, golden):
+    G.test_shard_restricts_frames(hostlib, golden, None)
+
+
+def test_no_device_means_no_reader(hostlib):
+    """the open fails loudly when the launch layer finds no device — there is nothing to fall back to (a fresh process:
+    readers parked by the tests above would bring their context along)"""
+    import sys
+    code = ("import libzseek_b200 as z, sys\n"
+            "img = open(sys.argv[1], 'rb').read()\n"
+            "try:\n    z.Reader(image=img)\n    print('opened')\n"
+            "except z.ZseekError as e:\n    print(e)\n")
+    env = dict(os.environ, ZSEEK_B200_LIB=HOSTEMU, ZSK_HOSTEMU_NO_DEVICE="1", PYTHONPATH=G.ROOT if hasattr(G, "ROOT") else os.path.dirname(emu_api.HERE))
+    out = subprocess.run([sys.executable, "-c", code, os.path.join(G.GOLDEN, "tiny_lz4.zsk")], env=env, capture_output=True, text=True, timeout=120)
+    assert out.stdout.strip() == "context creation failed: no CUDA device: emulated absence", (out.stdout, out.stderr[-300:])
+
+
+@pytest.mark.skipif(not have_reference(), reason="inputs come from the reference writer (oracle/_ref)")
+def test_cache_capacity_and_lru_order(hostlib):
+    """reference test/test_cache.c:135-159 restated for the HBM cache: capacity honoured, least recently used evicted,
+    a hit promotes (the same scenario as the GPU test, through a "device" buffer of the stand-in)."""
+    from datagen import refwriter, zsyn
+    data = zsyn.gen(140 * 8192, seed=5)
+    image = refwriter.write(data, ZSTD, 1, 8192)
+    cap = 66
+    L = hostlib.load_library()
+    buf = L.hostemu_device_alloc(8192)
+    try:
+        with hostlib.Reader(image=image, cache_size=cap) as rd:
+            assert rd.frames == 140
+            rd.load(0, rd.frames)
+
+            def read(f):
+                l0 = rd.launch_count
+                assert rd.pread_into(buf, 100, f * 8192 + 7) == 100
+                assert C.string_at(buf, 100) == data[f * 8192 + 7:f * 8192 + 107]
+                return rd.launch_count > l0       # True = a kernel ran = miss
+
+            order = list(range(2 * cap, -1, -2))[:cap + 1]        # cap + 1 distinct frames, never sequential
+            assert all(read(f) for f in order[:cap])
+            assert rd.stats().cached_frames == cap
+            assert not read(order[0])                             # hit: promoted to most recently used
+            assert read(order[cap])                               # one more frame evicts order[1]
+            assert rd.stats().cached_frames == cap
+            assert not read(order[0]) and not read(order[cap])
+            for f in order[2:cap]:
+                assert not read(f), f
+            assert read(order[1])                                 # the victim is gone
+            assert rd.stats().cached_frames == cap
+    finally:
+        L.hostemu_device_free(buf)
+
+
+def test_closed_readers_are_parked_and_reused(hostlib, golden):
+    """zseek_reader_close keeps the device side for the next open: after the first open / read / close cycle, later cycles
+    over other files allocate (almost) nothing new, and every reader still returns the right bytes."""
+    cases, _ = golden
+    L = hostlib.load_library()
+    names = ["tiny_zstd", "tiny_lz4", "zsyn_zstd3_256k_chunks", "tiny_zstd", "tiny_lz4", "zsyn_zstd3_256k_chunks"]
+    allocs = []
+    for name in names:
+        c = cases[name]
+        with OraclePort(c["image"]) as op:
+            want = op.decode_all().tobytes()
+        with hostlib.Reader(image=c["image"], cache_size=0) as rd:
+            n = min(5000, len(want))
+            assert rd.pread(n, 0)[1] == want[:n]
+            assert rd.read_range(len(want), 0) == want
+        allocs.append(int(L.hostemu_device_allocs()))
+    first = allocs[2]                      # every kind of file has been seen once
+    assert allocs[-1] - first <= 4, allocs  # re-opening them costs next to nothing
