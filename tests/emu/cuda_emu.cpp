@@ -6,6 +6,7 @@ namespace emu {
 
 Cta *g_cta = nullptr;
 static const size_t STACK = 256 << 10;
+static std::vector<char *> g_stacks; /* fiber stacks are recycled from launch to launch (a CTA of 416 threads would otherwise map and unmap 100 MB each time) */
 
 static void fiber_entry()
 {
@@ -27,7 +28,8 @@ static void run_cta(Cta &c)
     for (unsigned t = 0; t < n; t++) {
         Fiber &f = c.fibers[t];
         f.tid = t;
-        f.stack = (char *)malloc(STACK);
+        if (g_stacks.empty()) f.stack = (char *)malloc(STACK);
+        else { f.stack = g_stacks.back(); g_stacks.pop_back(); }
         getcontext(&f.ctx);
         f.ctx.uc_stack.ss_sp = f.stack;
         f.ctx.uc_stack.ss_size = STACK;
@@ -53,7 +55,7 @@ static void run_cta(Cta &c)
             abort();
         }
     }
-    for (auto &f : c.fibers) free(f.stack);
+    for (auto &f : c.fibers) g_stacks.push_back(f.stack);
     g_cta = nullptr;
 }
 

@@ -136,12 +136,12 @@ def test_corrupt_frame_fails_instead_of_hanging(lib, golden, torch_cuda):
             assert rd.pread(100, d1 + 5)[1] == good[d1 + 5:d1 + 105].tobytes()
 
 
-def test_sequential_scan_across_a_corrupt_frame(lib, golden, torch_cuda):
+def test_sequential_scan_across_a_corrupt_frame(lib, golden, torch_cuda, names=("zsyn_lz4_4k_chunks", "mix_zstd3"), cache_sizes=(0, 1)):
     """The read-ahead window of a sequential host scan may contain a bad frame far ahead of the one a call asks for.  The
     reference decodes only the requested frame (src/decompress.c:700-790): every good frame must still be served, only
     reads of the bad frame fail, and a retry gives the same verdict."""
     cases, _ = golden
-    for name in ("zsyn_lz4_4k_chunks", "mix_zstd3"):
+    for name in names:
         c = cases[name]
         with OraclePort(c["image"]) as op:
             good = op.decode_all()
@@ -161,7 +161,7 @@ def test_sequential_scan_across_a_corrupt_frame(lib, golden, torch_cuda):
                 except OSError:
                     ref_ok.append(False)
         assert not ref_ok[bad] and all(ref_ok[:bad]) and all(ref_ok[bad + 1:])
-        for cache_size in (0, 1):
+        for cache_size in cache_sizes:
             with lib.Reader(image=bytes(img), cache_size=cache_size) as rd:
                 off, failures = 0, 0
                 while off < len(good):
@@ -181,11 +181,11 @@ def test_sequential_scan_across_a_corrupt_frame(lib, golden, torch_cuda):
                 assert failures <= 1
 
 
-def test_host_batch_leaves_unproduced_bytes_untouched(lib, golden, torch_cuda):
+def test_host_batch_leaves_unproduced_bytes_untouched(lib, golden, torch_cuda, names=("mix_lz4", "zsyn_zstd3_128k")):
     """zseek_b200_pread_batch with a HOST destination stores exactly the bytes a loop of zseek_pread would store: stride
     gaps, the tail of reads clipped at a frame boundary, requests at/after EOF and count = 0 stay as they were."""
     cases, _ = golden
-    for name in ("mix_lz4", "zsyn_zstd3_128k"):
+    for name in names:
         c = cases[name]
         with OraclePort(c["image"]) as op:
             good = op.decode_all()
