@@ -265,3 +265,44 @@ def test_stream_ordered_batch_through_the_host_code(hostlib, golden, name):
             assert str(e.value).startswith("decompress frame")
             k = min(4096, int(op.d_off[1]) - 100)
             assert dst3.numpy()[:k].tobytes() == want[100:100 + k].tobytes()
+
+
+@pytest.mark.skipif(not have_reference(), reason="inputs come from the reference writer (oracle/_ref)")
+def test_scans_over_many_small_frames(hostlib):
+    """A forward scan whose read-ahead window grows (1, 8, 64 frames ...) while the next window is decoded behind the
+    caller's back, then reads that jump backwards (the window collapses, cached frames are served from HBM): every byte as
+    written, short reads exactly at the frame ends (B1)."""
+    from datagen import refwriter, zsyn
+    data = zsyn.gen(120 * 8192 + 1234, seed=9)
+    image = refwriter.write(data, ZSTD, 1, 8192)
+    with hostlib.Reader(image=image, cache_size=1) as rd:
+        assert rd.frames == 121
+        off, calls = 0, 0
+        while off < len(data):
+            r, b = rd.pread(3000, off)
+            want_r = min(3000, (off // 8192 + 1) * 8192 - off, len(data) - off)
+            assert r == want_r and b == data[off:off + r], off
+            off += r
+            calls += 1
+        assert rd.pread(3000, off) == (0, b"")
+        launches_forward = rd.launch_count
+        assert launches_forward < 40, launches_forward           # windows, not one launch per frame
+        for f in range(118, 60, -7):                             # backwards, never sequential
+            r, b = rd.pread(8192, f * 8192 + 100)
+            assert r == 8092 and b == data[f * 8192 + 100:(f + 1) * 8192]
+
+
+@pytest.mark.skipif(not have_reference(), reason="inputs come from the reference writer (oracle/_ref)")
+def test_host_range_read_in_many_pipeline_stages(hostlib, monkeypatch):
+    """zseek_b200_read_range into host memory is a pipeline of H2D / decode / D2H stages over chunks of frames; with the
+    stage size forced down to one frame the chunk arithmetic (staging halves, offsets, the ragged tail, a start in the
+    middle of a frame) is walked ~40 times instead of once."""
+    from datagen import refwriter, zsyn
+    data = zsyn.gen(40 * 8192 + 777, seed=3)
+    image = refwriter.write(data, ZSTD, 1, 8192)
+    monkeypatch.setenv("ZSEEK_B200_CHUNK_MB", "0")
+    monkeypatch.setenv("ZSEEK_B200_RAMP_MB", "0")
+    with hostlib.Reader(image=image, cache_size=0) as rd:
+        assert rd.read_range(len(data) + 50, 0) == data                      # short only at EOF
+        assert rd.read_range(100000, 12345) == data[12345:112345]
+        assert rd.read_range(10, len(data)) == b""
