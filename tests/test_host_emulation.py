@@ -306,3 +306,130 @@ def test_host_range_read_in_many_pipeline_stages(hostlib, monkeypatch):
         assert rd.read_range(len(data) + 50, 0) == data                      # short only at EOF
         assert rd.read_range(100000, 12345) == data[12345:112345]
         assert rd.read_range(10, len(data)) == b""
+
+
+@pytest.mark.skipif(not have_reference(), reason="inputs come from the reference writer (oracle/_ref)")
+FUZZ_STEPS = int(os.environ.get("ZSK_HOSTEMU_FUZZ_STEPS", "70"))          # soak runs: more steps, more seeds
+FUZZ_RUNS = [(1, 0), (2, 3)] + [(s, [0, 1, 5, 70][s % 4]) for s in range(3, 3 + int(os.environ.get("ZSK_HOSTEMU_FUZZ_EXTRA_SEEDS", "0")))]
+
+
+@pytest.mark.parametrize("seed,cache_size", FUZZ_RUNS)
+def test_random_sequences_of_calls_against_the_model(hostlib, monkeypatch, seed, cache_size):
+    """Differential state-machine test of reader.c: a sequence of randomly chosen calls on ONE reader — zseek_pread /
+    zseek_read with host and device buffers, multi-frame ranges, host and device batches, stream-ordered batches (with
+    other calls before the wait), cache_clear, unload / load, shard changes, with residency kicking in on the way — each
+    checked against the model the reference defines (B1-B4 over the writer's input).  What is tested is the interplay of
+    the cache (prefix-valid entries of partially decoded frames), windows, residency and shards."""
+    from datagen import refwriter, zsyn
+    monkeypatch.setenv("ZSEEK_B200_RESIDENT_AFTER", "9")
+    data = zsyn.gen(36 * 8192 + 4321, seed=40 + seed)
+    image = refwriter.write(data, ZSTD, 1, 8192)
+    total, F = len(data), 8192
+    L = hostlib.load_library()
+    rng = np.random.Generator(np.random.PCG64(seed))
+
+    def model(off, cnt, lo, hi):
+        """(result, bytes) of zseek_pread, or None when the frame is outside the shard [lo, hi)"""
+        if off >= total or cnt == 0:
+            return 0, b""
+        f = off // F
+        if not lo <= f < hi:
+            return None
+        n = min(cnt, min((f + 1) * F, total) - off)
+        return n, data[off:off + n]
+
+    with hostlib.Reader(image=image, cache_size=cache_size) as rd:
+        nfr = rd.frames
+        lo, hi, cursor = 0, nfr, 0
+        dev = _DevBuf(L, 1 << 20)
+        log = []
+        for step in range(FUZZ_STEPS):
+            b_lo, b_hi = lo * F, min(hi * F, total)
+            op = rng.choice(["pread", "pread", "pread", "pread_dev", "read", "range", "range_dev", "batch", "batch_dev", "async",
+                             "clear", "unload", "load", "shard", "stats", "frames"])
+            log.append(op)
+            try:
+                if op in ("pread", "pread_dev"):
+                    off = int(rng.integers(0, total + 100)) if rng.random() < 0.3 else int(rng.integers(b_lo, b_hi))
+                    cnt = int(rng.choice([0, 1, 100, 3000, 8192, 20000]))
+                    want = model(off, cnt, lo, hi)
+                    if want is None:
+                        with pytest.raises(hostlib.ZseekError) as e:
+                            rd.pread(cnt, off)
+                        assert "shard" in str(e.value)
+                    elif op == "pread":
+                        assert rd.pread(cnt, off) == want
+                    else:
+                        assert rd.pread_into(dev, cnt, off) == want[0] and dev.numpy()[:want[0]].tobytes() == want[1]
+                elif op == "read":
+                    cnt = int(rng.choice([1, 500, 9000]))
+                    want = model(cursor, cnt, lo, hi)
+                    if want is None:
+                        with pytest.raises(hostlib.ZseekError):
+                            rd.read(cnt)
+                    else:
+                        assert rd.read(cnt) == want
+                        cursor += want[0]
+                elif op in ("range", "range_dev"):
+                    off = int(rng.integers(b_lo, b_hi))
+                    cnt = int(rng.integers(0, min(60000, b_hi - off) + 1))
+                    if op == "range":
+                        assert rd.read_range(cnt, off) == data[off:off + cnt]
+                    else:
+                        assert rd.read_range_into(dev, cnt, off) == cnt and dev.numpy()[:cnt].tobytes() == data[off:off + cnt]
+                elif op in ("batch", "batch_dev", "async"):
+                    n = int(rng.integers(1, 60))
+                    offs = rng.integers(b_lo, b_hi, n).astype(np.uint64)
+                    if rng.random() < 0.3:
+                        offs[0] = total + 5                                                   # EOF inside a batch
+                    counts = rng.choice([0, 1, 700, 4096], n).astype(np.uint64)
+                    stride = 4200
+                    if op == "batch":
+                        dst = np.full(n * stride, 0x5A, dtype=np.uint8)
+                        res = rd.pread_batch(offs, counts=counts, dst=dst, dst_stride=stride)
+                        out = dst
+                    else:
+                        dev.upload(np.full(n * stride, 0x5A, dtype=np.uint8))
+                        if op == "batch_dev":
+                            res = rd.pread_batch(offs, counts=counts, dst=dev, dst_stride=stride)
+                        else:
+                            if not (lo == 0 and hi == nfr) or rng.random() < 0.5:
+                                rd.load(lo, hi)                                               # the shard must be resident
+                            else:
+                                rd.load(0, nfr)
+                            d_offs, d_counts, d_res = _DevBuf(L, 8 * n).upload(offs), _DevBuf(L, 8 * n).upload(counts), _DevBuf(L, 8 * n)
+                            rd.pread_batch_async(_DevBuf(L, n, keep=d_offs, addr=d_offs.addr), dev, dev_counts=d_counts, dst_stride=stride,
+                                                 dev_results=d_res)
+                            if rng.random() < 0.5:                                            # another call before the wait
+                                o2 = int(rng.integers(b_lo, b_hi))
+                                assert rd.pread(50, o2) == model(o2, 50, lo, hi)
+                            rd.batch_wait()
+                            res = np.frombuffer(C.string_at(d_res.addr, 8 * n), dtype=np.int64)
+                        out = dev.numpy()
+                    for i in range(n):
+                        r, b = model(int(offs[i]), int(counts[i]), lo, hi)
+                        assert res[i] == r, i
+                        assert out[i * stride:i * stride + r].tobytes() == b, i
+                        assert (out[i * stride + r:(i + 1) * stride] == 0x5A).all(), i
+                elif op == "clear":
+                    rd.cache_clear()
+                elif op == "unload":
+                    rd.unload()
+                elif op == "load":
+                    a = int(rng.integers(lo, hi))
+                    rd.load(a, int(rng.integers(a, hi)) + 1)
+                elif op == "shard":
+                    world = int(rng.choice([1, 1, 2, 3]))
+                    lo, hi = rd.set_shard(int(rng.integers(0, world)), world)
+                elif op == "stats":
+                    st = rd.stats()
+                    assert st.frames == nfr and st.decompressed_size == total and st.cached_frames <= max(cache_size, 64)
+                elif op == "frames":
+                    a = int(rng.integers(lo, hi))
+                    b = min(hi, a + int(rng.integers(1, 12)))
+                    nbytes = min(b * F, total) - a * F
+                    assert rd.decode_frames(a, b, dev) == nbytes and dev.numpy()[:nbytes].tobytes() == data[a * F:a * F + nbytes]
+            except AssertionError:
+                print("failing step", step, op, "after", log[-12:])
+                raise
+        assert rd.pread(10, lo * F)[1] == data[lo * F:lo * F + 10]
