@@ -308,11 +308,11 @@ def test_host_range_read_in_many_pipeline_stages(hostlib, monkeypatch):
         assert rd.read_range(10, len(data)) == b""
 
 
-@pytest.mark.skipif(not have_reference(), reason="inputs come from the reference writer (oracle/_ref)")
 FUZZ_STEPS = int(os.environ.get("ZSK_HOSTEMU_FUZZ_STEPS", "70"))          # soak runs: more steps, more seeds
 FUZZ_RUNS = [(1, 0), (2, 3)] + [(s, [0, 1, 5, 70][s % 4]) for s in range(3, 3 + int(os.environ.get("ZSK_HOSTEMU_FUZZ_EXTRA_SEEDS", "0")))]
 
 
+@pytest.mark.skipif(not have_reference(), reason="inputs come from the reference writer (oracle/_ref)")
 @pytest.mark.parametrize("seed,cache_size", FUZZ_RUNS)
 def test_random_sequences_of_calls_against_the_model(hostlib, monkeypatch, seed, cache_size):
     """Differential state-machine test of reader.c: a sequence of randomly chosen calls on ONE reader — zseek_pread /
