@@ -55,7 +55,7 @@ def test_emulated_zstd_bitstream_ring_across_a_4gib_address_boundary(emu, golden
     c = cases[name]
     with OraclePort(c["image"]) as op:
         payload = int(op.c_off[-1])
-        for wrap_at in list(range(16, payload, max(16, payload // 6))) + [payload - 7]:   # ~7 full decodes per file keep the CPU suite short
+        for wrap_at in list(range(16, payload, max(16, payload // 4))) + [payload - 7]:   # ~5 full decodes per file keep the CPU suite short
             out, status = emu_api.decode_all(emu, c["image"], op.codec, op.c_off, op.d_off, ctas=2, wrap_at=wrap_at)
             assert (status == 0).all(), (wrap_at, status)
             assert hashlib.sha256(out.tobytes()).hexdigest() == c["input_sha256"], wrap_at
@@ -296,7 +296,7 @@ def test_emulated_kernels_verify_checksums_like_the_reference(emu):
                     assert out.tobytes() == data
 
 
-@pytest.mark.parametrize("seed", [1, 2, 3])
+@pytest.mark.parametrize("seed", [1, 2])
 def test_emulated_lz4_kernels_on_random_mixtures(emu, seed):
     """Property check (decode == the writer's input) on randomly assembled data: runs of random length drawn from text,
     zeros, noise, short periods and far repeats, compressed by the reference writer at random frame sizes and levels; every
