@@ -2,6 +2,21 @@
  * (see cuda_emu.h). */
 #include "cuda_emu.h"
 
+#ifdef ZSK_EMU_FAST_SWITCH
+/* saves rbp, rbx, r12-r15 and the stack pointer of the running fiber, resumes the other one (System V x86-64) */
+__asm__(".text\n"
+        ".globl zsk_emu_switch\n"
+        ".hidden zsk_emu_switch\n"
+        ".type zsk_emu_switch,@function\n"
+        "zsk_emu_switch:\n"
+        "    pushq %rbp\n    pushq %rbx\n    pushq %r12\n    pushq %r13\n    pushq %r14\n    pushq %r15\n"
+        "    movq %rsp, (%rdi)\n"
+        "    movq (%rsi), %rsp\n"
+        "    popq %r15\n    popq %r14\n    popq %r13\n    popq %r12\n    popq %rbx\n    popq %rbp\n"
+        "    ret\n"
+        ".size zsk_emu_switch,.-zsk_emu_switch\n");
+#endif
+
 namespace emu {
 
 Cta *g_cta = nullptr;
@@ -15,7 +30,7 @@ static void fiber_entry()
     c.body();
     f->done = true;
     recheck();
-    swapcontext(&f->ctx, &c.sched);
+    zsk_emu_switch(&f->ctx, &c.sched);
 }
 
 static void run_cta(Cta &c)
@@ -30,11 +45,21 @@ static void run_cta(Cta &c)
         f.tid = t;
         if (g_stacks.empty()) f.stack = (char *)malloc(STACK);
         else { f.stack = g_stacks.back(); g_stacks.pop_back(); }
+#ifdef ZSK_EMU_FAST_SWITCH
+        /* first switch: six zeroed registers are popped, then `ret` enters fiber_entry with the stack aligned as after a call */
+        uintptr_t top = ((uintptr_t)f.stack + STACK) & ~(uintptr_t)15;
+        void **sp = (void **)(top - 8 * sizeof(void *));
+        for (int k = 0; k < 6; k++) sp[k] = nullptr;
+        sp[6] = (void *)fiber_entry;
+        sp[7] = nullptr; /* fiber_entry never returns: it switches back to the scheduler for good */
+        f.ctx.sp = sp;
+#else
         getcontext(&f.ctx);
         f.ctx.uc_stack.ss_sp = f.stack;
         f.ctx.uc_stack.ss_size = STACK;
         f.ctx.uc_link = &c.sched;
         makecontext(&f.ctx, (void (*)())fiber_entry, 0);
+#endif
     }
     for (;;) {
         bool any_live = false, progressed = false;
@@ -44,7 +69,7 @@ static void run_cta(Cta &c)
             any_live = true;
             if (f.wait != W_NONE && !f.released) continue;   /* parked */
             c.cur = &f;
-            swapcontext(&c.sched, &f.ctx);
+            zsk_emu_switch(&c.sched, &f.ctx);
             progressed = true;
         }
         if (!any_live) break;
