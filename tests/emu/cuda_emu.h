@@ -4,7 +4,7 @@
  * There is no GPU in the development container, and a gpurun round-trip costs minutes.  To debug the
  * LOGIC of the sm_100a kernels (format handling, warp-collective protocols, barrier placement) before
  * spending GPU time, tests/emu compiles the very same kernel source (libzseek_b200/csrc/zsk_kernels.cuh)
- * with g++ and runs each CUDA thread as a ucontext fiber:
+ * with g++ and runs each CUDA thread as a fiber (own stack, cooperative switch):
  *   - one CTA at a time, all of its threads as cooperatively scheduled fibers;
  *   - __syncthreads / __syncwarp / __shfl*_sync / __ballot_sync / __any/__all / __reduce_*_sync are
  *     rendezvous points: a fiber yields until every live lane named in the mask has arrived;

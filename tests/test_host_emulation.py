@@ -206,7 +206,7 @@ class _FakeTorch:
         return _DevBuf(self.L, n)
 
 
-@pytest.mark.parametrize("mode", ["hbm"])       # the pinned mode is what the state-machine test below goes through
+@pytest.mark.parametrize("mode", ["pinned", "hbm"])
 def test_random_host_readers_go_resident(hostlib, golden, mode, monkeypatch):
     """isolated misses -> the whole shard is decoded once, into a pinned window or (pinned budget spent) into HBM; reads from
     six threads, a device destination, and the way back through cache_clear — the GPU test's scenario on the stand-in"""
@@ -309,7 +309,7 @@ def test_host_range_read_in_many_pipeline_stages(hostlib, monkeypatch):
 
 
 FUZZ_STEPS = int(os.environ.get("ZSK_HOSTEMU_FUZZ_STEPS", "80"))          # soak runs: more steps, more seeds
-FUZZ_RUNS = [(2, 3)] + [(s, [0, 1, 5, 70][s % 4]) for s in range(3, 3 + int(os.environ.get("ZSK_HOSTEMU_FUZZ_EXTRA_SEEDS", "0")))]
+FUZZ_RUNS = [(1, 0), (2, 3)] + [(s, [0, 1, 5, 70][s % 4]) for s in range(3, 3 + int(os.environ.get("ZSK_HOSTEMU_FUZZ_EXTRA_SEEDS", "0")))]
 
 
 @pytest.mark.skipif(not have_reference(), reason="inputs come from the reference writer (oracle/_ref)")
