@@ -433,3 +433,10 @@ def test_random_sequences_of_calls_against_the_model(hostlib, monkeypatch, seed,
                 print("failing step", step, op, "after", log[-12:])
                 raise
         assert rd.pread(10, lo * F)[1] == data[lo * F:lo * F + 10]
+
+
+def test_concurrent_callers(hostlib, golden):
+    """twelve caller threads — scans and random reads on one SHARED reader plus readers of their own — as in the GPU test;
+    the stand-in serialises kernel launches, the locking of reader.c (reader mutex, residency read lock, parked readers,
+    process-wide budgets) runs as it does in the product (reference src/decompress.c:387,499: B10)"""
+    G.test_eight_concurrent_callers_on_one_reader(hostlib, golden, "zsyn_zstd3_128k", None)
